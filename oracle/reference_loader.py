@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference file by path.
+
+Only usable where /root/reference exists (the build container).  It never
+travels to the GPU box; what travels are the golden vectors generated from it
+(tests/golden/, made by oracle/make_golden.py) and the restatement in
+oracle/mapping_oracle.py which is asserted equal to it here.
+
+The reference module (vlnce_baselines/common/rgb_mapping.py) needs two shims
+to execute without Habitat / torch_scatter / a GPU:
+  * `torch_scatter.scatter_max` (third-party, pinned 2.0.6 in the reference's
+    SETUP.md:55-60, not vendored): stand-in implementing its published
+    semantics -- max-reduce along `dim`, positions nobody wrote are 0, the
+    arg output holds src.size(dim) for those (the reference discards it,
+    rgb_mapping.py:220).
+  * `torch.device("cuda", id)` hard-coded at rgb_mapping.py:14 -> CPU.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+
+REFERENCE_FILE = "/root/reference/vlnce_baselines/common/rgb_mapping.py"
+
+
+def reference_available() -> bool:
+    return os.path.isfile(REFERENCE_FILE)
+
+
+def _scatter_max(src, index, dim=-1, out=None, dim_size=None):
+    assert out is None
+    index = index.expand_as(src)
+    shape = list(src.shape)
+    shape[dim] = int(dim_size)
+    lowest = torch.finfo(src.dtype).min
+    res = torch.full(shape, lowest, dtype=src.dtype)
+    res.scatter_reduce_(dim, index, src, reduce="amax", include_self=True)
+    cnt = torch.zeros(shape, dtype=torch.int32)
+    cnt.scatter_add_(dim, index, torch.ones_like(index, dtype=torch.int32))
+    res = torch.where(cnt > 0, res, torch.zeros_like(res))
+    arg = torch.full(shape, src.size(dim), dtype=torch.long)
+    return res, arg
+
+
+class _Cfg:
+    def __init__(self, num_proc, resolution=0.12, egocentric_map_size=100,
+                 global_map_size=240, map_depth=64, gpu_id=0):
+        self.gpu_id = gpu_id
+        self.num_proc = num_proc
+        self.resolution = resolution
+        self.egocentric_map_size = egocentric_map_size
+        self.global_map_size = global_map_size
+        self.map_depth = map_depth
+
+
+def load_reference_module():
+    """exec the reference file with the torch_scatter stand-in installed."""
+    if not reference_available():
+        raise FileNotFoundError(REFERENCE_FILE)
+    if "torch_scatter" not in sys.modules:
+        ts = types.ModuleType("torch_scatter")
+        ts.scatter_max = _scatter_max
+        sys.modules["torch_scatter"] = ts
+    spec = importlib.util.spec_from_file_location("_ref_rgb_mapping", REFERENCE_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_reference_mapper(num_proc, **kw):
+    """Instantiate the reference RGBMapping on CPU."""
+    mod = load_reference_module()
+    real_device = torch.device
+
+    class _DevShim:
+        def __call__(self, *a, **k):
+            return real_device("cpu")
+
+        def __instancecheck__(self, obj):
+            return isinstance(obj, real_device)
+
+    orig = mod.torch.device
+    try:
+        mod.torch.device = lambda *a, **k: real_device("cpu")
+        m = mod.RGBMapping(_Cfg(num_proc, **kw))
+    finally:
+        mod.torch.device = orig
+    return m, mod
