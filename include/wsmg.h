@@ -1,0 +1,120 @@
+/*
+ * wsmg.h -- C ABI of libwsmg.so: the WS-MGMap per-step map update on B200 (sm_100a).
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python
+ * module vlnce_baselines/common/rgb_mapping.py::RGBMapping.
+ * These entry points are what that module's forward() binds to (through
+ * ctypes, see ws-mgmap_b200/_lib.py and INTEGRATION.md); each comment cites the
+ * reference lines the call replaces.  Plain pointers and sizes only; all
+ * `const float*` / `float*` arguments are DEVICE pointers unless a name ends
+ * in `_host`.  Every call is stream-ordered on `stream` (a cudaStream_t passed
+ * as void*), never synchronises the device, keeps no global mutable state and
+ * owns no memory: scratch is caller-allocated (wsmg_scratch_bytes).
+ *
+ * Return value: 0 = success; <0 = argument error (WSMG_E_*); >0 = cudaError_t
+ * of the failed runtime call / launch.  wsmg_error_string() decodes both.
+ */
+#ifndef WSMG_H_
+#define WSMG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSMG_ABI_VERSION 1
+
+enum {
+  WSMG_OK = 0,
+  WSMG_E_NULL = -1,        /* a required pointer is NULL                          */
+  WSMG_E_DIMS = -2,        /* non-positive / inconsistent dimension               */
+  WSMG_E_EGO_GT_GLOBAL = -3, /* egocentric map larger than the global map           */
+  WSMG_E_CHANNELS = -4,    /* channel count not supported                         */
+  WSMG_E_SMEM = -5,        /* geometry needs more shared memory than one SM has   */
+  WSMG_E_ALIGN = -6,       /* pointer not 16-byte aligned / Hf*Wf not multiple of 4 */
+  WSMG_E_SCRATCH = -7,     /* scratch buffer too small                            */
+  WSMG_E_BATCH = -8        /* bs larger than the map tensor's leading dimension   */
+};
+
+/* Geometry of one call.  Mirrors Mapping.__init__ (rgb_mapping.py:12-30) and the
+ * tensor shapes of RGBMapping.forward (rgb_mapping.py:79-90). */
+typedef struct wsmg_dims {
+  int32_t bs;      /* frames in this call (envs)                                  */
+  int32_t n_maps;  /* leading dim of the caller's full_global_map tensor (>= bs)   */
+  int32_t C;       /* map_depth: channels of features, global map and ego map      */
+  int32_t Hf, Wf;  /* feature frame (UNet proj_feat), NCHW                         */
+  int32_t Hd, Wd;  /* depth frame                                                  */
+  int32_t E;       /* egocentric_map_size (100)                                    */
+  int32_t G;       /* global_map_size (240)                                        */
+  double resolution; /* metres per cell (0.12)                                      */
+} wsmg_dims;
+
+int wsmg_abi_version(void);
+const char* wsmg_error_string(int code);
+
+/* Bytes of device scratch wsmg_map_update needs for `d` (packed cell codes + flags). */
+size_t wsmg_scratch_bytes(const wsmg_dims* d);
+
+/* Whole step: Mapping.project_feat_to_map (rgb_mapping.py:32-72) as called by
+ * RGBMapping.forward (rgb_mapping.py:85).
+ *   feat     [bs,C,Hf,Wf] fp32 NCHW          (rgb_features after the identity channel pool, :81-84)
+ *   depth    [bs,Hd,Wd,1] fp32 in [0,1]      (observations['depth']; the x10 of :37 is applied inside)
+ *   gps      [bs,2], compass [bs,1], mask [bs,1] fp32
+ *   gmap     [n_maps,G,G,C] fp32 NHWC        (self.full_global_map; rows [:bs] updated in place, :35,:56)
+ *   ego_out  [bs,C,E,E] fp32 NCHW            (final_retrieval, :70)
+ *   trig     optional [bs,4] = cos(-compass), sin(-compass), cos(compass), sin(compass) computed by
+ *            the caller (parity tests pass the CPU reference's values); NULL = sinf/cosf on device.
+ */
+int wsmg_map_update(const float* feat, const float* depth, const float* gps, const float* compass,
+                    const float* mask, float* gmap, float* ego_out, const float* trig,
+                    void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream);
+
+/* wsmg_map_update, additionally recording two CUDA events (cudaEvent_t passed as void*, either may
+ * be NULL) on `stream` immediately before and after the k_fused launch.  bench.py uses it to time the
+ * dominant kernel live for the roofline; results are identical to wsmg_map_update. */
+int wsmg_map_update_timed(const float* feat, const float* depth, const float* gps, const float* compass,
+                          const float* mask, float* gmap, float* ego_out, const float* trig,
+                          void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream,
+                          void* ev_before_fused, void* ev_after_fused);
+
+/* Stage: ComputeSpatialLocs.forward + the index half of ProjectToGroundPlane.forward
+ * (rgb_mapping.py:153-176, 188-217).  Outputs per sampled pixel of the Hf x Wf frame:
+ *   lin      [bs,Hf,Wf] int32  y_gp*E + x_gp, invalid writes forced to 0 (:207-208,:216)
+ *   invalid  [bs,Hf,Wf] uint8  1 = invalid_writes (:204)
+ */
+int wsmg_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid,
+                         const wsmg_dims* d, void* stream);
+
+/* Stage: scatter half of ProjectToGroundPlane.forward (rgb_mapping.py:210-232):
+ *   proj_out [bs,C,E,E] fp32 NCHW = proj_feats (before RotateTensor). */
+int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out,
+                     void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream);
+
+/* Stage: everything after the projection (rgb_mapping.py:35, 37(rotate via :267), 40-70):
+ * rotate(-compass), paste, translate, mask + max-fuse into gmap, translate back, crop, rotate(+compass).
+ *   proj_in  [bs,C,E,E] fp32 NCHW = proj_feats. */
+int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const float* compass,
+                                const float* mask, float* gmap, float* ego_out, const float* trig,
+                                const wsmg_dims* d, void* stream);
+
+/* Host helper: ATen's affine_grid base coordinates, linspace(-1,1,n)*(n-1)/n (align_corners=False),
+ * as torch-CPU produces them.  Used by tests to pin the in-kernel tables. */
+int wsmg_base_coords_host(float* out_host, int32_t n);
+
+/* End-to-end entry with HOST buffers (the call a trainer without device-resident
+ * observations makes): copies feat/depth/gps/compass/mask host->device, runs
+ * wsmg_map_update, copies ego_out device->host, all on `stream`, in env chunks so
+ * copies overlap compute.  gmap stays device-resident (it is state, rgb_mapping.py:29).
+ * `staging` is caller-allocated device memory of wsmg_host_staging_bytes(d, chunk) bytes. */
+size_t wsmg_host_staging_bytes(const wsmg_dims* d, int32_t chunk_envs);
+int wsmg_map_update_host(const float* feat_host, const float* depth_host, const float* gps_host,
+                         const float* compass_host, const float* mask_host, float* gmap,
+                         float* ego_out_host, void* staging, size_t staging_bytes,
+                         int32_t chunk_envs, const wsmg_dims* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSMG_H_ */

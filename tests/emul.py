@@ -1,0 +1,56 @@
+"""ctypes access to the host emulation of the kernels (test infrastructure)."""
+import ctypes
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+_pkg = importlib.import_module("ws-mgmap_b200")
+from wsmgmap_b200._lib import WsmgDims, make_dims  # noqa: E402
+from wsmgmap_b200.build import build_emulation  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build_emulation())
+        _lib.wsmg_emul_step.restype = ctypes.c_int
+        _lib.wsmg_emul_unproject_index.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def emul_cells(depth, hf, e=100, g=240, res=0.12):
+    bs, hd, wd = depth.shape
+    d = make_dims(bs, bs, 4, hf, hf, hd, wd, e, g, res)
+    lin = np.zeros((bs, hf, hf), np.int32)
+    inv = np.zeros((bs, hf, hf), np.uint8)
+    codes = np.zeros((bs, hf, hf), np.uint16)
+    rc = lib().wsmg_emul_unproject_index(_p(np.ascontiguousarray(depth)), _p(lin), _p(inv), _p(codes), ctypes.byref(d))
+    assert rc == 0, rc
+    return lin, inv.astype(bool), codes
+
+
+def emul_step(gmap, feat, depth, gps, compass, masks, trig=None, mode=0, proj_in=None, want_proj=False, e=100, g=240, res=0.12):
+    """gmap [n,G,G,C] updated in place.  trig [bs,4] or None.  Returns (ego, proj or None)."""
+    bs, c, hf, wf = feat.shape if feat is not None else (proj_in.shape[0], proj_in.shape[1], 4, 4)
+    hd, wd = (depth.shape[1], depth.shape[2]) if depth is not None else (4, 4)
+    d = make_dims(bs, gmap.shape[0] if gmap is not None else bs, c, hf, wf, hd, wd, e, g, res)
+    ego = np.zeros((bs, c, e, e), np.float32)
+    proj = np.zeros((bs, c, e, e), np.float32) if (want_proj or mode == 1) else None
+    arrs = [None if a is None else np.ascontiguousarray(a, np.float32) for a in (feat, depth, gps, compass, masks)]
+    trig_a = None if trig is None else np.ascontiguousarray(trig, np.float32)
+    pin = None if proj_in is None else np.ascontiguousarray(proj_in, np.float32)
+    rc = lib().wsmg_emul_step(_p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(gmap), _p(ego),
+                              _p(trig_a), _p(proj), _p(pin), ctypes.c_int(mode), ctypes.byref(d))
+    assert rc == 0, rc
+    return ego, proj

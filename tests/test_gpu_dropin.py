@@ -1,0 +1,94 @@
+"""Drop-in contract of the RGBMapping module: every interaction the reference's
+policy and trainers have with the module is replayed here against the oracle."""
+import types
+
+import pytest
+import torch
+
+from oracle.mapping_oracle import OracleMapper
+import wsmgmap_b200  # noqa: F401
+from wsmgmap_b200.rgb_mapping import RGBMapping
+from wsmgmap_b200.synth import make_depth, make_features
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def _cfg(num_proc, c=8):
+    return types.SimpleNamespace(gpu_id=0, num_proc=num_proc, resolution=0.12, egocentric_map_size=100,
+                                 global_map_size=240, map_depth=c)
+
+
+def _close(a, b, scale):
+    return ((a - b).abs() <= 1e-5 * b.abs() + 2e-5 * scale).all()
+
+
+def test_module_surface_and_state():
+    m = RGBMapping(_cfg(4))
+    assert isinstance(m, torch.nn.Module)
+    assert len(list(m.parameters())) == 0 and len(list(m.buffers())) == 0 and len(m.state_dict()) == 0
+    assert tuple(m.full_global_map.shape) == (4, 240, 240, 8) and m.full_global_map.device == DEV
+    assert tuple(m.agent_view.shape) == (4, 8, 240, 240)
+
+
+def test_forward_hook_rebinding_pause_and_cache():
+    c, hf, hd, n = 8, 64, 64, 4
+    m = RGBMapping(_cfg(n, c))
+    orc = OracleMapper(n, c)
+    seen = []
+    m.register_forward_hook(lambda mod, i, o: seen.append(o.cpu()))           # dagger_trainer.py:303-306,325-327
+    gen = torch.Generator().manual_seed(1)
+
+    def frame(bs):
+        return (make_features(bs, c, hf, hf, gen), make_depth("near", bs, hd, hd, gen),
+                torch.randn(bs, 2, generator=gen), torch.rand(bs, 1, generator=gen) * 6 - 3)
+
+    # trainers re-bind the state before a rollout (common_trainer.py:266-267, dagger_trainer.py:669-678)
+    m.full_global_map = torch.zeros([n] + list(m.full_global_map.shape[1:]), device=DEV)
+    m.agent_view = torch.zeros([n] + list(m.agent_view.shape[1:]), device=DEV)
+    feat, depth, gps, compass = frame(n)
+    obs = dict(depth=depth.to(DEV), gps=gps.to(DEV), compass=compass.to(DEV))
+    masks = torch.zeros(n, 1)
+    out = m(feat.to(DEV), obs, masks.to(DEV))
+    want = orc.step(feat, depth, gps, compass, masks)
+    assert obs["rgb_ego_map"] is out and tuple(out.shape) == (n, c, 100, 100)
+    assert _close(out.cpu(), want, 1.0) and _close(m.full_global_map.cpu(), orc.full_global_map, 1.0)
+    assert len(seen) == 1 and torch.equal(seen[0], out.cpu())
+    # cached path (rgb_mapping.py:80,87-88): features may be None
+    assert m(None, obs, masks.to(DEV)) is out
+    # _pause_envs: fancy-index the state to fewer envs and assign it back (common_trainer.py:171-172,476)
+    keep = [0, 2, 3]
+    m.full_global_map = m.full_global_map[keep]
+    orc.full_global_map = orc.full_global_map[keep]
+    feat, depth, gps, compass = frame(3)
+    obs = dict(depth=depth.to(DEV), gps=gps.to(DEV), compass=compass.to(DEV))
+    masks = torch.ones(3, 1)
+    out = m(feat.to(DEV), obs, masks.to(DEV))
+    want = orc.step(feat, depth, gps, compass, masks)
+    assert _close(out.cpu(), want, 1.0) and _close(m.full_global_map.cpu(), orc.full_global_map, 1.0)
+    # batch smaller than the state (rgb_mapping.py:35,56 touch rows [:bs] only)
+    before = m.full_global_map[2].clone()
+    feat, depth, gps, compass = frame(2)
+    obs = dict(depth=depth.to(DEV), gps=gps.to(DEV), compass=compass.to(DEV))
+    out = m(feat.to(DEV), obs, torch.ones(2, 1, device=DEV))
+    want = orc.step(feat, depth, gps, compass, torch.ones(2, 1))
+    assert _close(out.cpu(), want, 1.0) and torch.equal(m.full_global_map[2], before)
+    # secondary API returns (final_retrieval, the very same map tensor)
+    ego, gm = m.project_feat_to_map(feat.to(DEV), m.full_global_map, obs, torch.ones(2, 1, device=DEV))
+    assert gm is m.full_global_map and ego.shape == out.shape
+
+
+def test_channel_rebinning_and_input_checks():
+    m = RGBMapping(_cfg(2, 4))
+    gen = torch.Generator().manual_seed(2)
+    feat = make_features(2, 8, 32, 32, gen)                      # 8 channels pooled to map_depth 4 (rgb_mapping.py:82-84)
+    depth = make_depth("near", 2, 32, 32, gen)
+    obs = dict(depth=depth.to(DEV), gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
+    out = m(feat.to(DEV), obs, torch.zeros(2, 1, device=DEV))
+    orc = OracleMapper(2, 4)
+    pooled = torch.nn.functional.adaptive_max_pool1d(feat.permute(0, 2, 3, 1).reshape(2, -1, 8), 4)
+    pooled = pooled.reshape(2, 32, 32, 4).permute(0, 3, 1, 2)
+    want = orc.step(pooled, depth, torch.zeros(2, 2), torch.zeros(2, 1), torch.zeros(2, 1))
+    assert _close(out.cpu(), want, 1.0)
+    with pytest.raises(ValueError):
+        m(feat.to(DEV), dict(depth=depth, gps=obs["gps"], compass=obs["compass"]), torch.zeros(2, 1, device=DEV))  # CPU depth

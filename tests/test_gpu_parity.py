@@ -1,0 +1,221 @@
+"""Parity of the CUDA path (through the C ABI, ws-mgmap_b200/ops.py) with the oracle and the
+reference goldens.  Bars (BASELINE.json north_star):
+  * cell indices, invalid flags, occupancy bits, pre-rotation channel argmax: bit-exact
+    (argmax tie-break: lowest channel index; empty cell -> label 0);
+  * float maps: bit-exact when the oracle's sin/cos are supplied (`trig`), and within
+    |d| <= 1e-5*|ref| + 2e-5*max|feat| when sinf/cosf are evaluated on the device.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.mapping_oracle import MapGeometry, OracleMapper, spec_cells
+import wsmgmap_b200  # noqa: F401
+from wsmgmap_b200 import ops
+from wsmgmap_b200.synth import RandomWalk, make_depth, make_features
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _trig(compass):
+    c = compass[:, 0].cpu()
+    return torch.stack([torch.cos(-c), torch.sin(-c), torch.cos(c), torch.sin(c)], 1).contiguous()
+
+
+def _cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_golden_trajectory_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "traj_small.npz"))
+    bs, c, steps, hf = int(g["bs"]), int(g["c"]), int(g["steps"]), int(g["hf"])
+    gmap = torch.zeros(bs, 240, 240, c, device=DEV)
+    for t in range(steps):
+        feat, depth = _cu(g[f"feat{t}"]), _cu(g[f"depth{t}"]).unsqueeze(-1).contiguous()
+        trig = _cu(np.stack([g[f"cosneg{t}"], g[f"sinneg{t}"], g[f"cospos{t}"], g[f"sinpos{t}"]], 1))
+        lin, inv = ops.unproject_index(depth, hf, hf)
+        assert np.array_equal(lin.cpu().numpy().astype(np.int16), g[f"lin{t}"])
+        assert np.array_equal(np.packbits(inv.cpu().numpy()), g[f"invalid{t}"])
+        proj = ops.scatter_max(feat, depth)
+        assert np.array_equal(proj.cpu().numpy(), g[f"proj{t}"])
+        ego = ops.map_update(feat, depth, _cu(g[f"gps{t}"]), _cu(g[f"compass{t}"]), _cu(g[f"masks{t}"]), gmap, trig=trig)
+        assert np.array_equal(ego.cpu().numpy(), g[f"ego{t}"]), f"step {t}"
+        assert _sha(gmap.cpu().numpy()) == str(g[f"mapsha{t}"]), f"step {t}"
+    assert np.array_equal(gmap.cpu().numpy(), g["map_final"])
+
+
+def test_golden_frame_real_shapes(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frame_real.npz"))
+    bs, c, hf, hd = int(g["bs"]), int(g["c"]), int(g["hf"]), int(g["hd"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    feat = make_features(bs, c, hf, hf, gen)
+    depth = make_depth("uniform", bs, hd, hd, gen)
+    if _sha(feat.numpy()) != str(g["feat_sha"]):
+        pytest.skip("torch RNG stream differs from the golden file's")
+    trig = _cu(np.stack([g["cosneg"], g["sinneg"], g["cospos"], g["sinpos"]], 1))
+    gmap = torch.zeros(bs, 240, 240, c, device=DEV)
+    lin, inv = ops.unproject_index(depth.to(DEV), hf, hf)
+    assert np.array_equal(lin.cpu().numpy().astype(np.int16), g["lin"])
+    assert np.array_equal(np.packbits(inv.cpu().numpy()), g["invalid"])
+    proj = ops.scatter_max(feat.to(DEV), depth.to(DEV)).cpu().numpy()
+    assert _sha(proj) == str(g["proj_sha"])
+    assert np.array_equal(proj[0].argmax(0).astype(np.uint8), g["argmax"])
+    assert np.array_equal(np.packbits((proj[0] != 0).any(0)), g["occupied"])
+    ego = ops.map_update(feat.to(DEV), depth.to(DEV), _cu(g["gps"]), _cu(g["compass"]), torch.zeros(bs, 1, device=DEV),
+                         gmap, trig=trig)
+    assert _sha(ego.cpu().numpy()) == str(g["ego_sha"])
+    assert _sha(gmap.cpu().numpy()) == str(g["map_sha"])
+
+
+def test_trajectory_100_steps_vs_oracle():
+    """BASELINE config 3: 100-step random-walk trajectory, 8 envs, real shapes, checked every step."""
+    bs, c, hf, hd, steps = 8, 64, 224, 256, 100
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    orc = OracleMapper(bs, c)
+    gmap = torch.zeros(bs, 240, 240, c, device=DEV)
+    gmap_dev_trig = torch.zeros(bs, 240, 240, c, device=DEV)
+    walk = RandomWalk(bs, seed=42, far_env=7)
+    resets = {b: 20 + 9 * b for b in range(bs)}
+    kinds = ("uniform", "near", "room2", "room4")
+    worst = 0.0
+    for t in range(steps):
+        gps, compass, masks = walk.step()
+        for b, when in resets.items():
+            if t == when:
+                masks[b] = 0.0
+        gen = torch.Generator().manual_seed(1000 * t)
+        feat = make_features(bs, c, hf, hf, gen, signed=(t % 10 == 3))
+        depth = torch.cat([make_depth(kinds[(t + b) % 4], 1, hd, hd, gen) for b in range(bs)], 0)
+        want = orc.step(feat, depth, gps, compass, masks, keep=True)
+        fd, dd = feat.to(DEV), depth.to(DEV)
+        lin, inv = ops.unproject_index(dd, hf, hf)
+        assert torch.equal(lin.cpu().long(), orc.last["lin"]), f"step {t}: cell indices"
+        assert torch.equal(inv.cpu(), orc.last["invalid"]), f"step {t}: invalid flags"
+        if t % 10 == 0:
+            proj = ops.scatter_max(fd, dd).cpu()
+            assert torch.equal(proj, orc.last["proj"]), f"step {t}: projected grid"
+            assert torch.equal(proj.argmax(1), orc.last["proj"].argmax(1)), f"step {t}: channel argmax"
+            occ = (proj != 0).any(1).reshape(bs, -1)
+            assert torch.equal(occ, orc.last["occ"]), f"step {t}: occupancy"   # U(0,1)/N(0,1) features are never exactly 0
+        ego = ops.map_update(fd, dd, gps.to(DEV), compass.to(DEV), masks.to(DEV), gmap, trig=_trig(compass).to(DEV))
+        assert torch.equal(ego.cpu(), want), f"step {t}: ego map (oracle trig)"
+        assert torch.equal(gmap.cpu(), orc.full_global_map), f"step {t}: global map (oracle trig)"
+        ego2 = ops.map_update(fd, dd, gps.to(DEV), compass.to(DEV), masks.to(DEV), gmap_dev_trig)
+        tol = 1e-5 * want.abs() + 2e-5 * feat.abs().max()
+        err = (ego2.cpu() - want).abs()
+        assert (err <= tol).all(), f"step {t}: ego map (device trig) max err {err.max().item()}"
+        gerr = (gmap_dev_trig.cpu() - orc.full_global_map).abs()
+        assert (gerr <= 1e-5 * orc.full_global_map.abs() + 2e-5 * feat.abs().max()).all(), f"step {t}: global map (device trig)"
+        worst = max(worst, err.max().item())
+    print(f"device-trig worst abs deviation over the trajectory: {worst:.3e}")
+
+
+@pytest.mark.parametrize("c,hf,hd,e,gl,res", [(27, 32, 32, 100, 240, 0.12), (4, 40, 48, 61, 150, 0.2), (64, 256, 256, 100, 240, 0.12)])
+def test_other_geometries_vs_spec(c, hf, hd, e, gl, res):
+    from oracle.mapping_oracle import spec_step
+    geo = MapGeometry(resolution=res, ego=e, glob=gl)
+    bs = 2
+    gen = torch.Generator().manual_seed(c + e)
+    walk = RandomWalk(bs, seed=e, reset_prob=0.25)
+    gmap = torch.zeros(bs, gl, gl, c, device=DEV)
+    g_spec = np.zeros((bs, gl, gl, c), np.float32)
+    for t in range(3):
+        gps, compass, masks = walk.step()
+        gps = gps * (res / 0.12)
+        feat = make_features(bs, c, hf, hf, gen, signed=(t == 1))
+        depth = make_depth(("near", "uniform", "room2")[t], bs, hd, hd, gen) * (res / 0.12)
+        trig = _trig(compass)
+        lin, inv = ops.unproject_index(depth.to(DEV), hf, hf, e, gl, res)
+        slin, sinv = spec_cells(depth[..., 0].numpy(), hf, hf, geo)
+        assert np.array_equal(lin.cpu().numpy(), slin) and np.array_equal(inv.cpu().numpy(), sinv)
+        ego = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), masks.to(DEV), gmap, e=e,
+                             resolution=res, trig=trig.to(DEV))
+        tr = trig.numpy()
+        sego, _ = spec_step(g_spec, feat.numpy(), depth[..., 0].numpy(), gps.numpy(), compass.numpy(), masks[:, 0].numpy(),
+                            dict(neg=(tr[:, 0], tr[:, 1]), pos=(tr[:, 2], tr[:, 3])), geo)
+        assert np.array_equal(ego.cpu().numpy(), sego)
+        assert np.array_equal(gmap.cpu().numpy(), g_spec)
+
+
+def test_stage_composition_and_host_pipeline():
+    bs, c, hf, hd = 5, 64, 224, 256
+    gen = torch.Generator().manual_seed(77)
+    feat = make_features(bs, c, hf, hf, gen)
+    depth = make_depth("room4", bs, hd, hd, gen)
+    gps = torch.randn(bs, 2, generator=gen)
+    compass = torch.rand(bs, 1, generator=gen) * 6 - 3
+    masks = torch.zeros(bs, 1)
+    g1 = torch.zeros(bs + 2, 240, 240, c, device=DEV)        # bs < n_maps: rows [bs:] stay untouched
+    g1[bs:] = 3.0
+    ego1 = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), masks.to(DEV), g1)
+    assert (g1[bs:] == 3.0).all()
+    proj = ops.scatter_max(feat.to(DEV), depth.to(DEV))
+    g2 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego2 = ops.register_fuse_retrieve(proj, gps.to(DEV), compass.to(DEV), masks.to(DEV), g2)
+    assert torch.equal(ego1, ego2) and torch.equal(g1[:bs], g2)
+    # host-buffer entry (pinned), chunked: same result
+    d = ops.dims_for(feat.shape, depth.shape, bs)
+    pipe = ops.HostPipeline(d, DEV, chunk_envs=2)
+    g3 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego_h = torch.empty(bs, c, 100, 100).pin_memory()
+    pipe.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g3, ego_h)
+    torch.cuda.synchronize()
+    assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g3, g2)
+
+
+def test_full_size_properties():
+    """Size-independent properties at a batch the oracle would need minutes for (256 envs):
+    max-fusion is idempotent, the map is monotone, a reset forgets everything, batch order is irrelevant."""
+    bs, c, hf, hd = 256, 64, 224, 256
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    feat = torch.rand(bs, c, hf, hf, generator=gen, device=DEV)
+    depth = torch.rand(bs, hd, hd, 1, generator=gen, device=DEV) * 0.6
+    gps = torch.randn(bs, 2, generator=gen, device=DEV) * 3
+    compass = torch.rand(bs, 1, generator=gen, device=DEV) * 6 - 3
+    ones, zeros = torch.ones(bs, 1, device=DEV), torch.zeros(bs, 1, device=DEV)
+    gmap = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego_a = ops.map_update(feat, depth, gps, compass, zeros, gmap)
+    snap = gmap.clone()
+    ego_b = ops.map_update(feat, depth, gps, compass, ones, gmap)          # same frame again
+    assert torch.equal(gmap, snap) and torch.equal(ego_a, ego_b)            # idempotent
+    feat2 = torch.rand(bs, c, hf, hf, generator=gen, device=DEV)
+    ops.map_update(feat2, depth, gps + 0.3, compass + 0.2, ones, gmap)
+    assert (gmap >= snap).all() and (gmap >= 0).all()                         # monotone, non-negative
+    ego_c = ops.map_update(feat, depth, gps, compass, zeros, gmap)          # reset forgets
+    assert torch.equal(gmap, snap) and torch.equal(ego_c, ego_a)
+    perm = torch.randperm(bs, device=DEV)
+    g2 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego_p = ops.map_update(feat[perm].contiguous(), depth[perm].contiguous(), gps[perm].contiguous(),
+                           compass[perm].contiguous(), zeros, g2)
+    assert torch.equal(ego_p, ego_a[perm]) and torch.equal(g2, snap[perm])   # envs independent
+    # linearity of the bilinear stages in the features: scaling features by 2 scales everything by 2 exactly
+    g3 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego_2 = ops.map_update(feat * 2, depth, gps, compass, zeros, g3)
+    assert torch.equal(ego_2, ego_a * 2) and torch.equal(g3, snap * 2)
+
+
+def test_error_codes():
+    import ctypes
+    from wsmgmap_b200 import _lib
+    lib = _lib.load()
+    d = _lib.make_dims(1, 1, 64, 224, 224, 256, 256, 100, 240, 0.12)
+    assert lib.wsmg_map_update(None, None, None, None, None, None, None, None, None, 0, ctypes.byref(d), None) == -1
+    bad = _lib.make_dims(1, 1, 64, 224, 224, 256, 256, 300, 240, 0.12)
+    assert lib.wsmg_scratch_bytes(ctypes.byref(bad)) == 0
+    x = torch.zeros(16, device=DEV)
+    assert lib.wsmg_unproject_index(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(x.data_ptr()),
+                                    ctypes.c_void_p(x.data_ptr()), ctypes.byref(bad), None) == -3
+    big = _lib.make_dims(1, 1, 64, 224, 224, 256, 256, 200, 480, 0.12)     # fan + crop do not fit one SM
+    feat = torch.zeros(1, 64, 224, 224, device=DEV)
+    depth = torch.zeros(1, 256, 256, 1, device=DEV)
+    with pytest.raises(_lib.WsmgError, match="shared memory"):
+        ops.map_update(feat, depth, torch.zeros(1, 2, device=DEV), torch.zeros(1, 1, device=DEV),
+                       torch.zeros(1, 1, device=DEV), torch.zeros(1, 480, 480, 64, device=DEV), e=200)

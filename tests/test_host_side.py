@@ -1,0 +1,71 @@
+"""CPU-only checks of the host side: the C ABI library loads and exports every symbol the
+header declares, host helpers agree with torch, and get_grid keeps the reference's contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import wsmgmap_b200  # noqa: F401
+from wsmgmap_b200 import _lib
+from wsmgmap_b200.rgb_mapping import get_grid, to_grid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    header = open(os.path.join(ROOT, "include", "wsmg.h")).read()
+    declared = set(re.findall(r"\b(wsmg_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/wsmg.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.wsmg_abi_version() == 1
+    assert b"NULL" in lib.wsmg_error_string(-1)
+
+
+def test_validation_without_gpu():
+    lib = _lib.load()
+    ok = _lib.make_dims(8, 8, 64, 224, 224, 256, 256, 100, 240, 0.12)
+    assert lib.wsmg_scratch_bytes(ctypes.byref(ok)) >= 8 * 224 * 224 * 2
+    for bad in (_lib.make_dims(0, 8, 64, 224, 224, 256, 256, 100, 240, 0.12),
+                _lib.make_dims(8, 4, 64, 224, 224, 256, 256, 100, 240, 0.12),
+                _lib.make_dims(8, 8, 64, 224, 224, 256, 256, 300, 240, 0.12),
+                _lib.make_dims(8, 8, 64, 223, 223, 256, 256, 100, 240, 0.12)):
+        assert lib.wsmg_scratch_bytes(ctypes.byref(bad)) == 0
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 100, 101, 224, 240, 480])
+def test_base_coords_match_torch(n):
+    out = np.zeros(n, np.float32)
+    assert _lib.load().wsmg_base_coords_host(out.ctypes.data_as(ctypes.c_void_p), n) == 0
+    want = (torch.linspace(-1, 1, n) * (n - 1) / n).numpy()
+    assert np.array_equal(out, want)
+
+
+def test_get_grid_contract():
+    pose = torch.tensor([[0.25, -0.5, 0.3], [0.0, 0.0, -2.0]])
+    rot, trans = get_grid(pose, (2, 1, 12, 12), "cpu")
+    assert rot.shape == (2, 12, 12, 2) and trans.shape == (2, 12, 12, 2)
+    base = torch.linspace(-1, 1, 12) * 11 / 12
+    assert torch.equal(trans[0, :, :, 0], (base + 0.25)[None, :].expand(12, 12))
+    assert torch.equal(trans[0, :, :, 1], (base - 0.5)[:, None].expand(12, 12))
+    from oracle.reference_loader import load_reference_module, reference_available
+    if reference_available():
+        r2, t2 = load_reference_module().get_grid(pose, (2, 1, 12, 12), "cpu")
+        assert torch.equal(rot, r2) and torch.equal(trans, t2)
+    tg = to_grid(240, -14.399999999999999, 14.399999999999999)
+    gx, gy = tg.get_grid_coords(torch.tensor([[0.0, 0.0], [1.37, -2.21]]))
+    assert gx.tolist() == [120.0, 109.0] and gy.tolist() == [120.0, 102.0]
+
+
+def test_product_path_has_no_oracle_import():
+    pkg = os.path.join(ROOT, "ws-mgmap_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,137 @@
+"""The CUDA kernels' CTA body and pixel math, compiled for the host (csrc/wsmg_emul.cpp),
+against the reference goldens and the elementwise spec.  Catches index / layout / schedule
+bugs here, where there is no GPU; the -m gpu tests then check the real kernels."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from emul import emul_cells, emul_step, lib
+from oracle.mapping_oracle import MapGeometry, spec_cells, spec_step
+import wsmgmap_b200  # noqa: F401
+from wsmgmap_b200._lib import make_dims
+from wsmgmap_b200.synth import RandomWalk, make_depth, make_features
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _trig(compass):
+    c = torch.as_tensor(compass)[:, 0]
+    return np.stack([torch.cos(-c).numpy(), torch.sin(-c).numpy(), torch.cos(c).numpy(), torch.sin(c).numpy()], 1)
+
+
+def _trig_dict(tr):
+    return dict(neg=(tr[:, 0], tr[:, 1]), pos=(tr[:, 2], tr[:, 3]))
+
+
+def test_golden_trajectory_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "traj_small.npz"))
+    bs, c, steps, hf = int(g["bs"]), int(g["c"]), int(g["steps"]), int(g["hf"])
+    gmap = np.zeros((bs, 240, 240, c), np.float32)
+    for t in range(steps):
+        trig = np.stack([g[f"cosneg{t}"], g[f"sinneg{t}"], g[f"cospos{t}"], g[f"sinpos{t}"]], 1)
+        lin, inv, codes = emul_cells(g[f"depth{t}"], hf)
+        assert np.array_equal(lin.astype(np.int16), g[f"lin{t}"])
+        assert np.array_equal(np.packbits(inv), g[f"invalid{t}"])
+        assert not (codes == 0xFFFE).any()
+        ego, proj = emul_step(gmap, g[f"feat{t}"], g[f"depth{t}"], g[f"gps{t}"], g[f"compass{t}"], g[f"masks{t}"],
+                              trig=trig, want_proj=True)
+        assert np.array_equal(proj, g[f"proj{t}"])
+        assert np.array_equal(ego, g[f"ego{t}"])
+        assert _sha(gmap) == str(g[f"mapsha{t}"])
+
+
+def test_golden_frame_real_shapes(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frame_real.npz"))
+    bs, c, hf, hd = int(g["bs"]), int(g["c"]), int(g["hf"]), int(g["hd"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    feat = make_features(bs, c, hf, hf, gen).numpy()
+    depth = make_depth("uniform", bs, hd, hd, gen)[..., 0].numpy()
+    if _sha(feat) != str(g["feat_sha"]):
+        pytest.skip("torch RNG stream differs from the golden file's")
+    trig = np.stack([g["cosneg"], g["sinneg"], g["cospos"], g["sinpos"]], 1)
+    gmap = np.zeros((bs, 240, 240, c), np.float32)
+    ego, proj = emul_step(gmap, feat, depth, g["gps"], g["compass"], np.zeros((bs, 1), np.float32), trig=trig, want_proj=True)
+    assert _sha(proj) == str(g["proj_sha"])
+    assert np.array_equal(proj[0].argmax(0).astype(np.uint8), g["argmax"])
+    assert _sha(ego) == str(g["ego_sha"])
+    assert _sha(gmap) == str(g["map_sha"])
+
+
+@pytest.mark.parametrize("c,hf,hd,e,gl,res", [
+    (27, 32, 32, 100, 240, 0.12),     # channels not a multiple of 4: scalar map path, ragged last slab
+    (4, 40, 48, 61, 150, 0.2),        # odd ego size, different resolution
+    (6, 24, 24, 30, 64, 0.3),         # small even geometry
+])
+def test_general_geometry_matches_spec(c, hf, hd, e, gl, res):
+    geo = MapGeometry(resolution=res, ego=e, glob=gl)
+    bs = 2
+    gen = torch.Generator().manual_seed(c * 7 + e)
+    walk = RandomWalk(bs, seed=e, reset_prob=0.25)
+    g_emul = np.zeros((bs, gl, gl, c), np.float32)
+    g_spec = np.zeros((bs, gl, gl, c), np.float32)
+    for t in range(4):
+        gps, compass, masks = walk.step()
+        gps = gps * (res / 0.12)
+        if t == 3:
+            gps[0] += torch.tensor([0.45 * gl * res, -0.48 * gl * res])     # window clipped by the map border
+        feat = make_features(bs, c, hf, hf, gen, signed=(t % 2 == 0)).numpy()
+        depth = make_depth(("near", "uniform", "room2", "near")[t], bs, hd, hd, gen)[..., 0].numpy() * (res / 0.12)
+        trig = _trig(compass)
+        lin, inv, _ = emul_cells(depth, hf, e, gl, res)
+        slin, sinv = spec_cells(depth, hf, hf, geo)
+        assert np.array_equal(lin, slin) and np.array_equal(inv, sinv)
+        ego, proj = emul_step(g_emul, feat, depth, gps.numpy(), compass.numpy(), masks.numpy(), trig=trig,
+                              want_proj=True, e=e, g=gl, res=res)
+        sego, inter = spec_step(g_spec, feat, depth, gps.numpy(), compass.numpy(), masks[:, 0].numpy(), _trig_dict(trig), geo)
+        assert np.array_equal(proj, inter["proj"])
+        assert np.array_equal(ego, sego)
+        assert np.array_equal(g_emul, g_spec)
+
+
+def test_stage_entry_points_compose():
+    """scatter-only then registration-only equals the whole step."""
+    bs, c, hf, hd = 2, 8, 48, 64
+    gen = torch.Generator().manual_seed(3)
+    feat = make_features(bs, c, hf, hf, gen, signed=True).numpy()
+    depth = make_depth("near", bs, hd, hd, gen)[..., 0].numpy()
+    gps = np.array([[0.3, -0.2], [1.5, 2.5]], np.float32)
+    compass = np.array([[0.4], [-2.0]], np.float32)
+    masks = np.zeros((bs, 1), np.float32)
+    trig = _trig(compass)
+    g1 = np.zeros((bs, 240, 240, c), np.float32)
+    ego1, _ = emul_step(g1, feat, depth, gps, compass, masks, trig=trig)
+    _, proj = emul_step(None, feat, depth, gps, compass, masks, mode=1)
+    g2 = np.zeros((bs, 240, 240, c), np.float32)
+    ego2, _ = emul_step(g2, None, None, gps, compass, masks, trig=trig, mode=2, proj_in=proj)
+    assert np.array_equal(ego1, ego2) and np.array_equal(g1, g2)
+
+
+def test_shared_memory_plan_fits_b200():
+    import ctypes
+    d = make_dims(8, 8, 64, 224, 224, 256, 256, 100, 240, 0.12)
+    total = lib().wsmg_emul_smem_bytes(ctypes.byref(d))
+    assert 0 < total <= 227 * 1024, total
+    assert lib().wsmg_emul_fan_cells(ctypes.byref(d)) == 2748
+
+
+def test_device_trig_tolerance_statement():
+    """With sinf/cosf evaluated in-kernel (trig=None) instead of the oracle's values the result moves
+    by a few ulp of the rotation matrix; the documented bound is |d| <= 1e-5*|ref| + 2e-5*max|feat|."""
+    bs, c, hf, hd = 2, 4, 56, 64
+    gen = torch.Generator().manual_seed(9)
+    feat = make_features(bs, c, hf, hf, gen).numpy()
+    depth = make_depth("room2", bs, hd, hd, gen)[..., 0].numpy()
+    gps = np.array([[0.7, 0.1], [-1.2, 0.9]], np.float32)
+    compass = np.array([[1.234], [-0.777]], np.float32)
+    masks = np.zeros((bs, 1), np.float32)
+    ga = np.zeros((bs, 240, 240, c), np.float32)
+    gb = np.zeros((bs, 240, 240, c), np.float32)
+    ea, _ = emul_step(ga, feat, depth, gps, compass, masks, trig=_trig(compass))
+    eb, _ = emul_step(gb, feat, depth, gps, compass, masks, trig=None)       # libm sinf/cosf
+    tol = 1e-5 * np.abs(ea) + 2e-5 * np.abs(feat).max()
+    assert (np.abs(ea - eb) <= tol).all()

@@ -1,0 +1,70 @@
+"""ctypes binding of libwsmg.so (C ABI in include/wsmg.h).  No fallback: if the library or
+a CUDA device is missing, the product path raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwsmg.so")
+
+
+class WsmgDims(ctypes.Structure):
+    _fields_ = [
+        ("bs", ctypes.c_int32), ("n_maps", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("Hf", ctypes.c_int32), ("Wf", ctypes.c_int32), ("Hd", ctypes.c_int32), ("Wd", ctypes.c_int32),
+        ("E", ctypes.c_int32), ("G", ctypes.c_int32), ("resolution", ctypes.c_double),
+    ]
+
+
+_P = ctypes.c_void_p
+_DP = ctypes.POINTER(WsmgDims)
+
+SIGNATURES = {
+    "wsmg_abi_version": (ctypes.c_int, []),
+    "wsmg_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "wsmg_scratch_bytes": (ctypes.c_size_t, [_DP]),
+    "wsmg_map_update": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
+    "wsmg_map_update_timed": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P, _P, _P]),
+    "wsmg_unproject_index": (ctypes.c_int, [_P, _P, _P, _DP, _P]),
+    "wsmg_scatter_max": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
+    "wsmg_register_fuse_retrieve": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _DP, _P]),
+    "wsmg_base_coords_host": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "wsmg_host_staging_bytes": (ctypes.c_size_t, [_DP, ctypes.c_int32]),
+    "wsmg_map_update_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP, _P]),
+}
+
+_lib = None
+
+
+class WsmgError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libwsmg.so (building it in-tree if the sources are newer / it is missing and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from .build import build_cuda
+        build_cuda()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.wsmg_abi_version() != 1:
+        raise WsmgError(f"libwsmg ABI {lib.wsmg_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().wsmg_error_string(rc)
+        raise WsmgError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def make_dims(bs, n_maps, c, hf, wf, hd, wd, e, g, resolution) -> WsmgDims:
+    return WsmgDims(int(bs), int(n_maps), int(c), int(hf), int(wf), int(hd), int(wd), int(e), int(g), float(resolution))

@@ -1,0 +1,74 @@
+"""In-tree build of the native libraries (no torch involved, plain nvcc / g++).
+
+    python ws-mgmap_b200/build.py            # libwsmg.so (sm_100a) + test-only emulation
+The .so files land in ws-mgmap_b200/lib/ (git-ignored, shipped to the GPU box by gpurun).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "lib")
+ROOT = os.path.dirname(HERE)
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",                 # FMAs only where the arithmetic contract writes fmaf()
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+]
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources():
+    out = [os.path.join(ROOT, "include", "wsmg.h")]
+    for f in sorted(os.listdir(CSRC)):
+        out.append(os.path.join(CSRC, f))
+    return out
+
+
+def build_cuda(verbose: bool = False, force: bool = False) -> str:
+    os.makedirs(LIB, exist_ok=True)
+    target = os.path.join(LIB, "libwsmg.so")
+    if not force and _newer(target, _sources()):
+        return target
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", target, os.path.join(CSRC, "wsmg.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return target
+
+
+def build_emulation(force: bool = False) -> str:
+    """Host emulation of the kernels -- test infrastructure, see csrc/wsmg_emul.cpp."""
+    os.makedirs(LIB, exist_ok=True)
+    target = os.path.join(LIB, "libwsmg_emul.so")
+    if not force and _newer(target, _sources()):
+        return target
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-fno-fast-math",
+           "-I", os.path.join(ROOT, "include"), "-o", target, os.path.join(CSRC, "wsmg_emul.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return target
+
+
+if __name__ == "__main__":
+    v = "-v" in sys.argv
+    print(build_cuda(verbose=v, force="-f" in sys.argv))
+    print(build_emulation(force="-f" in sys.argv))

@@ -1,0 +1,316 @@
+// libwsmg.so -- WS-MGMap per-step map update for B200 (sm_100a).  C ABI in include/wsmg.h.
+//
+// Three launches per step, all on the caller's stream:
+//   k_reset   episode-reset mask over the whole NHWC map       (rgb_mapping.py:35)
+//   k_cells   fused unproject + height-band test + bin + index  (rgb_mapping.py:153-176, 188-217)
+//   k_fused   one CTA per (env, 4-channel slab): shared-memory scatter-max, rotate, translate,
+//             max-fuse into the map window, translate back, crop, rotate -> NCHW ego map
+//             (rgb_mapping.py:210-232, 37-70).  Body in wsmg_body.h.
+// No tensor cores: the path is gather / scatter-max / bilinear streaming (~0.3 flop/byte).
+#include <cuda_runtime.h>
+
+#include "wsmg_body.h"
+#include "wsmg_host.h"
+
+namespace wsmg {
+
+constexpr int FUSED_THREADS = 1024;
+constexpr int CELLS_THREADS = 256;
+
+// ------------------------------------------------------------------ k_reset
+// full_global_map[:bs] *= masks (rgb_mapping.py:35).  mask == 1 (the steady state) touches nothing.
+__global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
+                                               size_t per_env) {
+  const int b = blockIdx.y;
+  const float m = mask[b];
+  if (m == 1.0f) return;
+  float* base = gmap + (size_t)b * per_env;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((per_env & 3) == 0) {
+    float4* b4 = reinterpret_cast<float4*>(base);
+    const size_t n4 = per_env >> 2;
+    if (m == 0.0f) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (; i < n4; i += stride) b4[i] = z;
+    } else {
+      for (; i < n4; i += stride) {
+        float4 v = b4[i];
+        v.x *= m; v.y *= m; v.z *= m; v.w *= m;
+        b4[i] = v;
+      }
+    }
+  } else {
+    for (; i < per_env; i += stride) base[i] = (m == 0.0f) ? 0.0f : base[i] * m;
+  }
+}
+
+// ------------------------------------------------------------------ k_cells
+// One thread per sampled pixel of the Hf x Wf frame.  Writes the packed fan code the fused
+// kernel scatters with and/or the reference-shaped (linear index, invalid) pair of the stage API.
+__global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
+                                                          int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
+                                                          Geo g) {
+  __shared__ int rowoff[160];
+  for (int t = threadIdx.x; t < g.fan_rows; t += blockDim.x) {
+    int off = 0;
+    for (int y = 0; y < t; ++y) off += fan_row_width(y, g.E);
+    rowoff[t] = off;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int HW = g.Hf * g.Wf;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= HW) return;
+  const int i = t / g.Wf, j = t - i * g.Wf;
+  int x, y;
+  const bool ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
+  if (codes != nullptr) {
+    uint16_t code = CODE_INVALID;
+    if (ok) {
+      if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code = (uint16_t)(rowoff[y] + x - fan_x_lo(y));
+      else code = CODE_OUTLIER;
+    }
+    codes[(size_t)b * HW + t] = code;
+  }
+  if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
+  if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------ k_fused
+template <bool VEC>
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  fused_body<VEC>(p, blockIdx.x, smem, threadIdx.x, blockDim.x);
+}
+
+// ------------------------------------------------------------------ host glue
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_reset(float* gmap, const float* mask, const wsmg_dims* d, cudaStream_t s) {
+  const size_t per_env = (size_t)d->G * d->G * d->C;
+  dim3 grid(148 * 2, d->bs);
+  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env);
+  return (int)cudaGetLastError();
+}
+
+static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, const Geo& g, int bs,
+                        cudaStream_t s) {
+  if (g.fan_rows > 160) return WSMG_E_DIMS;
+  const int HW = g.Hf * g.Wf;
+  dim3 grid((HW + CELLS_THREADS - 1) / CELLS_THREADS, bs);
+  k_cells<<<grid, CELLS_THREADS, 0, s>>>(depth, codes, lin, invalid, g);
+  return (int)cudaGetLastError();
+}
+
+static int launch_fused(const FusedParams& p, cudaStream_t s) {
+  const SmemPlan sp = make_plan(p.g);
+  int dev = 0, max_optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (sp.total > max_optin) return WSMG_E_SMEM;
+  const bool vec = (p.g.C % 4) == 0;
+  const int slabs = (p.g.C + SLAB - 1) / SLAB;
+  if (vec) {
+    e = cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total);
+    if (e != cudaSuccess) return (int)e;
+    k_fused<true><<<p.bs * slabs, FUSED_THREADS, sp.total, s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total);
+    if (e != cudaSuccess) return (int)e;
+    k_fused<false><<<p.bs * slabs, FUSED_THREADS, sp.total, s>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace wsmg
+
+using namespace wsmg;
+
+extern "C" {
+
+int wsmg_abi_version(void) { return WSMG_ABI_VERSION; }
+
+const char* wsmg_error_string(int code) {
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  const char* s = error_string(code);
+  return s ? s : "unknown wsmg error";
+}
+
+size_t wsmg_scratch_bytes(const wsmg_dims* d) {
+  if (validate_dims(d) != WSMG_OK) return 0;
+  return scratch_bytes(d);
+}
+
+int wsmg_base_coords_host(float* out_host, int32_t n) {
+  if (out_host == nullptr) return WSMG_E_NULL;
+  if (n <= 0) return WSMG_E_DIMS;
+  base_coords_host(out_host, n);
+  return WSMG_OK;
+}
+
+static int map_update_impl(const float* feat, const float* depth, const float* gps, const float* compass,
+                           const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
+                           size_t scratch_bytes_, const wsmg_dims* d, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+  int rc = validate_dims(d);
+  if (rc != WSMG_OK) return rc;
+  if (!feat || !depth || !gps || !compass || !mask || !gmap || !ego_out || !scratch) return WSMG_E_NULL;
+  if (!aligned16(feat) || !aligned16(gmap) || !aligned16(scratch)) return WSMG_E_ALIGN;
+  if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
+  const Geo g = make_geo(d);
+  rc = launch_reset(gmap, mask, d, s);
+  if (rc) return rc;
+  uint16_t* codes = (uint16_t*)scratch;
+  rc = launch_cells(depth, codes, nullptr, nullptr, g, d->bs, s);
+  if (rc) return rc;
+  FusedParams p{};
+  p.feat = feat; p.codes = codes; p.gps = gps; p.compass = compass; p.trig = trig;
+  p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
+  p.stop_after_scatter = 0; p.bs = d->bs; p.g = g;
+  if (ev0) cudaEventRecord(ev0, s);
+  rc = launch_fused(p, s);
+  if (ev1) cudaEventRecord(ev1, s);
+  return rc;
+}
+
+int wsmg_map_update(const float* feat, const float* depth, const float* gps, const float* compass,
+                    const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
+                    size_t scratch_bytes_, const wsmg_dims* d, void* stream) {
+  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, trig, scratch, scratch_bytes_, d,
+                         (cudaStream_t)stream, nullptr, nullptr);
+}
+
+int wsmg_map_update_timed(const float* feat, const float* depth, const float* gps, const float* compass,
+                          const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
+                          size_t scratch_bytes_, const wsmg_dims* d, void* stream, void* ev_before_fused,
+                          void* ev_after_fused) {
+  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, trig, scratch, scratch_bytes_, d,
+                         (cudaStream_t)stream, (cudaEvent_t)ev_before_fused, (cudaEvent_t)ev_after_fused);
+}
+
+int wsmg_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid, const wsmg_dims* d, void* stream) {
+  int rc = validate_dims(d);
+  if (rc != WSMG_OK) return rc;
+  if (!depth || !lin || !invalid) return WSMG_E_NULL;
+  return launch_cells(depth, nullptr, lin, invalid, make_geo(d), d->bs, (cudaStream_t)stream);
+}
+
+int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out, void* scratch, size_t scratch_bytes_,
+                     const wsmg_dims* d, void* stream) {
+  int rc = validate_dims(d);
+  if (rc != WSMG_OK) return rc;
+  if (!feat || !depth || !proj_out || !scratch) return WSMG_E_NULL;
+  if (!aligned16(feat) || !aligned16(scratch)) return WSMG_E_ALIGN;
+  if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Geo g = make_geo(d);
+  uint16_t* codes = (uint16_t*)scratch;
+  rc = launch_cells(depth, codes, nullptr, nullptr, g, d->bs, s);
+  if (rc) return rc;
+  FusedParams p{};
+  p.feat = feat; p.codes = codes; p.proj_out = proj_out; p.stop_after_scatter = 1; p.bs = d->bs; p.g = g;
+  return launch_fused(p, s);
+}
+
+int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const float* compass, const float* mask,
+                                float* gmap, float* ego_out, const float* trig, const wsmg_dims* d, void* stream) {
+  int rc = validate_dims(d);
+  if (rc != WSMG_OK) return rc;
+  if (!proj_in || !gps || !compass || !mask || !gmap || !ego_out) return WSMG_E_NULL;
+  if (!aligned16(gmap)) return WSMG_E_ALIGN;
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = launch_reset(gmap, mask, d, s);
+  if (rc) return rc;
+  FusedParams p{};
+  p.proj_in = proj_in; p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap; p.ego = ego_out;
+  p.bs = d->bs; p.g = make_geo(d);
+  return launch_fused(p, s);
+}
+
+// ------------------------------------------------------------------ host-buffer entry
+// staging layout per chunk slot (2 slots): feat | depth | gps | compass | mask | ego | scratch
+struct HostSlot { float *feat, *depth, *gps, *compass, *mask, *ego; void* scratch; size_t scratch_bytes; };
+
+static size_t slot_bytes(const wsmg_dims* d, int chunk, HostSlot* out, unsigned char* base) {
+  wsmg_dims dc = *d; dc.bs = chunk; dc.n_maps = chunk > d->n_maps ? chunk : d->n_maps;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  size_t o_feat = take((size_t)chunk * d->C * d->Hf * d->Wf * 4);
+  size_t o_depth = take((size_t)chunk * d->Hd * d->Wd * 4);
+  size_t o_gps = take((size_t)chunk * 2 * 4);
+  size_t o_comp = take((size_t)chunk * 4);
+  size_t o_mask = take((size_t)chunk * 4);
+  size_t o_ego = take((size_t)chunk * d->C * d->E * d->E * 4);
+  size_t sb = scratch_bytes(&dc);
+  size_t o_scr = take(sb);
+  if (out && base) {
+    out->feat = (float*)(base + o_feat); out->depth = (float*)(base + o_depth); out->gps = (float*)(base + o_gps);
+    out->compass = (float*)(base + o_comp); out->mask = (float*)(base + o_mask); out->ego = (float*)(base + o_ego);
+    out->scratch = base + o_scr; out->scratch_bytes = sb;
+  }
+  return off;
+}
+
+size_t wsmg_host_staging_bytes(const wsmg_dims* d, int32_t chunk_envs) {
+  if (validate_dims(d) != WSMG_OK || chunk_envs <= 0) return 0;
+  int chunk = chunk_envs < d->bs ? chunk_envs : d->bs;
+  return 2 * slot_bytes(d, chunk, nullptr, nullptr);
+}
+
+int wsmg_map_update_host(const float* feat_host, const float* depth_host, const float* gps_host,
+                         const float* compass_host, const float* mask_host, float* gmap, float* ego_out_host,
+                         void* staging, size_t staging_bytes, int32_t chunk_envs, const wsmg_dims* d, void* stream) {
+  int rc = validate_dims(d);
+  if (rc != WSMG_OK) return rc;
+  if (!feat_host || !depth_host || !gps_host || !compass_host || !mask_host || !gmap || !ego_out_host || !staging)
+    return WSMG_E_NULL;
+  if (chunk_envs <= 0) return WSMG_E_DIMS;
+  const int chunk = chunk_envs < d->bs ? chunk_envs : d->bs;
+  if (staging_bytes < wsmg_host_staging_bytes(d, chunk) || !aligned16(staging)) return WSMG_E_SCRATCH;
+  cudaStream_t user = (cudaStream_t)stream;
+  // two internal streams ping-pong over the two staging slots so that the copies of chunk i+1
+  // overlap the kernels of chunk i; both are fenced against the caller's stream with events.
+  cudaStream_t st[2];
+  cudaEvent_t fork, join[2];
+  cudaError_t e;
+  if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+  }
+  cudaEventRecord(fork, user);
+  cudaStreamWaitEvent(st[0], fork, 0);
+  cudaStreamWaitEvent(st[1], fork, 0);
+  const size_t one = slot_bytes(d, chunk, nullptr, nullptr);
+  const size_t per_map = (size_t)d->G * d->G * d->C;
+  int slot = 0;
+  for (int b0 = 0; b0 < d->bs && rc == 0; b0 += chunk, slot ^= 1) {
+    const int n = (d->bs - b0) < chunk ? (d->bs - b0) : chunk;
+    HostSlot hs;
+    slot_bytes(d, chunk, &hs, (unsigned char*)staging + slot * one);
+    cudaStream_t s = st[slot];
+    const size_t fe = (size_t)d->C * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
+    cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(hs.compass, compass_host + b0, n * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(hs.mask, mask_host + b0, n * 4, cudaMemcpyHostToDevice, s);
+    wsmg_dims dc = *d; dc.bs = n; dc.n_maps = n;
+    rc = wsmg_map_update(hs.feat, hs.depth, hs.gps, hs.compass, hs.mask, gmap + b0 * per_map, hs.ego, nullptr,
+                         hs.scratch, hs.scratch_bytes, &dc, s);
+    if (rc == 0) cudaMemcpyAsync(ego_out_host + b0 * ee, hs.ego, n * ee * 4, cudaMemcpyDeviceToHost, s);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventRecord(join[i], st[i]);
+    cudaStreamWaitEvent(user, join[i], 0);
+  }
+  // streams/events are released once their work drains (CUDA defers destruction)
+  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(st[i]); cudaEventDestroy(join[i]); }
+  cudaEventDestroy(fork);
+  if (rc == 0) rc = (int)cudaGetLastError();
+  return rc;
+}
+
+}  // extern "C"

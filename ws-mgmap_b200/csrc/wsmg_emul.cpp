@@ -1,0 +1,90 @@
+// TEST INFRASTRUCTURE ONLY -- serial host emulation of the CUDA kernels.
+// Compiles the very same CTA body (wsmg_body.h) and pixel math (wsmg_math.h) with g++ and
+// runs every "thread" in order (tid0 = 0, stride = 1), so the CPU test-suite can check the
+// index arithmetic, the packed-fan layout, the band/ring schedule and the in-place hazards
+// against the oracle without a GPU.  It cannot find races; the GPU parity tests do that.
+// Not linked into libwsmg.so and not reachable from the product API.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+struct uint2 { unsigned x, y; };
+
+#include "wsmg_body.h"
+#include "wsmg_host.h"
+
+using namespace wsmg;
+
+extern "C" {
+
+int wsmg_emul_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid, uint16_t* codes, const wsmg_dims* d) {
+  int rc = validate_dims(d);
+  if (rc) return rc;
+  const Geo g = make_geo(d);
+  std::vector<int> rowoff(g.fan_rows + 1, 0);
+  for (int y = 0; y < g.fan_rows; ++y) rowoff[y + 1] = rowoff[y] + fan_row_width(y, g.E);
+  const int HW = g.Hf * g.Wf;
+  for (int b = 0; b < d->bs; ++b)
+    for (int t = 0; t < HW; ++t) {
+      int i = t / g.Wf, j = t - i * g.Wf, x, y;
+      bool ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
+      if (codes) {
+        uint16_t code = CODE_INVALID;
+        if (ok) {
+          if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code = (uint16_t)(rowoff[y] + x - fan_x_lo(y));
+          else code = CODE_OUTLIER;
+        }
+        codes[(size_t)b * HW + t] = code;
+      }
+      if (lin) lin[(size_t)b * HW + t] = y * g.E + x;
+      if (invalid) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
+    }
+  return 0;
+}
+
+// mode: 0 = whole step, 1 = scatter only (proj_out), 2 = registration only (proj_in)
+int wsmg_emul_step(const float* feat, const float* depth, const float* gps, const float* compass, const float* mask,
+                   float* gmap, float* ego_out, const float* trig, float* proj_out, const float* proj_in, int mode,
+                   const wsmg_dims* d) {
+  int rc = validate_dims(d);
+  if (rc) return rc;
+  const Geo g = make_geo(d);
+  const SmemPlan sp = make_plan(g);
+  const int HW = g.Hf * g.Wf;
+  std::vector<uint16_t> codes((size_t)d->bs * HW);
+  if (mode != 2) wsmg_emul_unproject_index(depth, nullptr, nullptr, codes.data(), d);
+  if (mode != 1) {
+    const size_t per_env = (size_t)g.G * g.G * g.C;
+    for (int b = 0; b < d->bs; ++b) {
+      float m = mask[b];
+      if (m == 1.0f) continue;
+      for (size_t i = 0; i < per_env; ++i) gmap[b * per_env + i] = (m == 0.0f) ? 0.0f : gmap[b * per_env + i] * m;
+    }
+  }
+  FusedParams p{};
+  p.feat = feat; p.codes = codes.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
+  p.ego = ego_out; p.proj_out = proj_out; p.proj_in = (mode == 2) ? proj_in : nullptr;
+  p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g;
+  std::vector<unsigned char> smem(sp.total + 16);
+  unsigned char* sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+  const int slabs = (g.C + SLAB - 1) / SLAB;
+  for (int blk = 0; blk < d->bs * slabs; ++blk) {
+    memset(sm, 0xCD, sp.total);     // poison: nothing may rely on zeroed shared memory
+    if (g.C % 4 == 0) fused_body<true>(p, blk, sm, 0, 1);
+    else fused_body<false>(p, blk, sm, 0, 1);
+  }
+  return 0;
+}
+
+int wsmg_emul_smem_bytes(const wsmg_dims* d) {
+  if (validate_dims(d)) return -1;
+  return make_plan(make_geo(d)).total;
+}
+
+int wsmg_emul_fan_cells(const wsmg_dims* d) {
+  if (validate_dims(d)) return -1;
+  return make_geo(d).fan_cells;
+}
+
+}  // extern "C"

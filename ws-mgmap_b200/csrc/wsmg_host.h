@@ -1,0 +1,76 @@
+// Host-side helpers shared by the CUDA library (wsmg.cu) and the emulation (wsmg_emul.cpp):
+// argument validation and the geometry constants, produced the way the reference's
+// Python produces them (double arithmetic, one cast to fp32 at the point of use).
+#pragma once
+#include <math.h>
+
+#include "../../include/wsmg.h"
+#include "wsmg_math.h"
+
+namespace wsmg {
+
+inline int validate_dims(const wsmg_dims* d) {
+  if (d == nullptr) return WSMG_E_NULL;
+  if (d->bs <= 0 || d->C <= 0 || d->Hf <= 0 || d->Wf <= 0 || d->Hd <= 0 || d->Wd <= 0 || d->E <= 0 || d->G <= 0 ||
+      !(d->resolution > 0.0))
+    return WSMG_E_DIMS;
+  if (d->Hd != d->Wd || d->Hf != d->Wf) return WSMG_E_DIMS;   // the reference assumes square frames (rgb_mapping.py:149-151,189)
+  if (d->E > d->G) return WSMG_E_EGO_GT_GLOBAL;
+  if (d->n_maps < d->bs) return WSMG_E_BATCH;
+  if ((d->Hf * d->Wf) % 4 != 0) return WSMG_E_ALIGN;
+  if (d->E > 254 || d->G > 32768) return WSMG_E_DIMS;          // packed fan codes are 16 bit
+  return WSMG_OK;
+}
+
+inline Geo make_geo(const wsmg_dims* d) {
+  Geo g;
+  g.E = d->E; g.G = d->G; g.C = d->C; g.Hf = d->Hf; g.Wf = d->Wf; g.Hd = d->Hd; g.Wd = d->Wd;
+  const double cmin = -(double)d->G * d->resolution / 2;       // rgb_mapping.py:21
+  const double cmax = (double)d->G * d->resolution / 2;        // rgb_mapping.py:22
+  g.cmax = (float)cmax;
+  g.cmin = (float)cmin;
+  g.cell = (float)((cmax - cmin) / (double)d->G);              // rgb_mapping.py:98 == :146
+  g.half = (float)((d->E - 1) / 2.0);                          // rgb_mapping.py:173
+  const double t45 = tan(45.0 * (M_PI / 180.0));               // np.tan(np.deg2rad(fov/2)), fov = 90
+  g.cx = (float)(d->Hd / 2.0);                                 // rgb_mapping.py:149
+  g.cy = (float)(d->Wd / 2.0);
+  g.fx = (float)((d->Hd / 2.0) / t45);                         // rgb_mapping.py:150
+  g.fy = (float)((d->Wd / 2.0) / t45);
+  g.ksub = (float)((double)d->Wd / (double)d->Wf);             // rgb_mapping.py:189
+  g.half_e = (float)d->E / 2.0f;
+  g.half_g = (float)d->G / 2.0f;
+  g.gcenter = (float)(d->G / 2);                               // G//2
+  g.paste_lo = d->G / 2 - d->E / 2;                            // rgb_mapping.py:42
+  int ymax = d->E / 2;                                         // rint((E-1)/2 - a) <= ceil((E-1)/2) for a > 0
+  g.fan_rows = ymax + 1 < d->E ? ymax + 1 : d->E;
+  g.fan_cells = 0;
+  for (int y = 0; y < g.fan_rows; ++y) g.fan_cells += fan_row_width(y, d->E);
+  return g;
+}
+
+inline const char* error_string(int code) {
+  switch (code) {
+    case WSMG_OK: return "success";
+    case WSMG_E_NULL: return "a required pointer is NULL";
+    case WSMG_E_DIMS: return "non-positive or inconsistent dimension";
+    case WSMG_E_EGO_GT_GLOBAL: return "egocentric map larger than the global map";
+    case WSMG_E_CHANNELS: return "channel count not supported";
+    case WSMG_E_SMEM: return "geometry needs more shared memory than one SM provides";
+    case WSMG_E_ALIGN: return "pointer not 16-byte aligned or Hf*Wf not a multiple of 4";
+    case WSMG_E_SCRATCH: return "scratch buffer too small";
+    case WSMG_E_BATCH: return "bs larger than the map tensor's leading dimension";
+    default: return nullptr;
+  }
+}
+
+// scratch layout: [bs * Hf*Wf] uint16 packed cell codes
+inline size_t scratch_bytes(const wsmg_dims* d) {
+  size_t codes = (size_t)d->bs * d->Hf * d->Wf * sizeof(uint16_t);
+  return (codes + 255) & ~(size_t)255;
+}
+
+inline void base_coords_host(float* out, int n) {
+  for (int j = 0; j < n; ++j) out[j] = base_coord(j, n);
+}
+
+}  // namespace wsmg

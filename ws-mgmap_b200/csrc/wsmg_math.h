@@ -1,0 +1,140 @@
+// Exact fp32 arithmetic of the map update, shared by the CUDA kernels (wsmg.cu) and
+// the host emulation used by the CPU tests (wsmg_emul.cpp).  Every rounding here is
+// deliberate: it reproduces what the reference's PyTorch-CPU ops compute
+// (reference vlnce_baselines/common/rgb_mapping.py; ATen affine_grid / grid_sampler),
+// see oracle/mapping_oracle.py `spec_*` for the numpy statement of the same math.
+// Build with contraction OFF (nvcc -fmad=false, g++ -ffp-contract=off): FMAs appear
+// only where written.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WSMG_HD __host__ __device__ __forceinline__
+#else
+#define WSMG_HD inline
+#endif
+
+namespace wsmg {
+
+constexpr uint16_t CODE_INVALID = 0xFFFFu;   // pixel does not write (rgb_mapping.py:204)
+constexpr uint16_t CODE_OUTLIER = 0xFFFEu;   // valid pixel outside the packed fan (depth < 0)
+constexpr float SENTINEL = -1e16f;           // rgb_mapping.py:187
+
+// ---------------------------------------------------------------- geometry constants
+struct Geo {
+  int E, G, C, Hf, Wf, Hd, Wd;
+  int paste_lo;          // G/2 - floor(E/2)                      rgb_mapping.py:42
+  int fan_rows;          // rows of the ego grid a depth >= 0 pixel can reach
+  int fan_cells;         // packed cells of the fan
+  float cmax, cmin;      // +-G*res/2 as fp32                      rgb_mapping.py:21-22
+  float cell;            // (cmax-cmin)/G as fp32 (== 0.12f)       rgb_mapping.py:98,146
+  float half;            // (E-1)/2                                rgb_mapping.py:173
+  float cx, cy, fx, fy;  // pinhole, 90 deg FoV                    rgb_mapping.py:148-151
+  float ksub;            // Wd / Wf                                rgb_mapping.py:189
+  float half_e, half_g;  // E/2, G/2 (grid_sampler scaling factor)
+  float gcenter;         // G//2                                   rgb_mapping.py:47
+};
+
+// Packed "fan" layout of the scatter grid.  With depth >= 0 and the 90 degree pinhole
+// (|xx| <= 1), a pixel that lands in row y = rint(half - Z/cell) has
+// x = rint(half + xx*Z/cell) in [y-1, E-y]; one guard cell is kept on each side.
+WSMG_HD int fan_x_lo(int y) { return y - 2 > 0 ? y - 2 : 0; }
+WSMG_HD int fan_x_hi(int y, int E) { return E - y + 1 < E - 1 ? E - y + 1 : E - 1; }   // inclusive
+WSMG_HD int fan_row_width(int y, int E) {
+  int w = fan_x_hi(y, E) - fan_x_lo(y) + 1;
+  return w > 0 ? w : 0;
+}
+
+// ---------------------------------------------------------------- order-preserving keys
+WSMG_HD uint32_t f2key(float f) {
+#if defined(__CUDA_ARCH__)
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b; __builtin_memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+WSMG_HD float key2f(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(b);
+#else
+  float f; __builtin_memcpy(&f, &b, 4); return f;
+#endif
+}
+// key 0 = "no valid pixel".  Final value per rgb_mapping.py:220-230: empty -> 0,
+// == -1e16 -> 0, otherwise x + 0*(x+1e16) which only turns -0.0 into +0.0.
+WSMG_HD float finish_cell(uint32_t k) {
+  if (k == 0u) return 0.0f;
+  float v = key2f(k);
+  return (v == SENTINEL) ? 0.0f : v + 0.0f;
+}
+
+// ---------------------------------------------------------------- affine_grid / grid_sampler
+// linspace(-1,1,n)[j] * (n-1) / n with torch-CPU's symmetric FMA linspace.
+WSMG_HD float base_coord(int j, int n) {
+  if (n == 1) return 0.0f;
+  float step = 2.0f / (float)(n - 1);
+  float lin = (j < n / 2) ? fmaf(step, (float)j, -1.0f) : fmaf(-step, (float)(n - 1 - j), 1.0f);
+  return (lin * (float)(n - 1)) / (float)n;
+}
+// ((g+1)*size-1)/2 as the vectorised CPU kernel evaluates it: fma(g+1, size/2, -0.5).
+WSMG_HD float unnormalize(float g, float half_size) { return fmaf(g + 1.0f, half_size, -0.5f); }
+
+struct Tap1D { int i0; float w1; };   // taps i0 (weight 1-w1) and i0+1 (weight w1)
+WSMG_HD Tap1D make_tap(float coord) {
+  float f0 = floorf(coord);
+  Tap1D t; t.i0 = (int)f0; t.w1 = coord - f0; return t;
+}
+// r = a*nw; r = fma(b,ne,r); r = fma(c,sw,r); r = fma(d,se,r)   (nw,ne,sw,se order)
+WSMG_HD float blend4(float a, float b, float c, float d, float nw, float ne, float sw, float se) {
+  float r = a * nw;
+  r = fmaf(b, ne, r);
+  r = fmaf(c, sw, r);
+  r = fmaf(d, se, r);
+  return r;
+}
+struct Weights { float nw, ne, sw, se; };
+WSMG_HD Weights make_weights(float wx, float wy) {
+  float ex = 1.0f - wx, ey = 1.0f - wy;
+  Weights w; w.nw = ey * ex; w.ne = ey * wx; w.sw = wy * ex; w.se = wy * wx; return w;
+}
+
+// Rotation grid of RotateTensor (rgb_mapping.py:242-248) through MKL's K=3 bmm:
+// gx = fma(y, sin, x*cos); gy = fma(y, cos, x*(-sin)).
+WSMG_HD void rot_coords(float bx, float by, float cs, float sn, float half_size, float* ix, float* iy) {
+  float gx = fmaf(by, sn, bx * cs);
+  float gy = fmaf(by, cs, bx * (-sn));
+  *ix = unnormalize(gx, half_size);
+  *iy = unnormalize(gy, half_size);
+}
+
+// ---------------------------------------------------------------- pose -> global cell
+// to_grid.get_grid_coords (rgb_mapping.py:100-103); half-to-even.
+WSMG_HD void gps_cell(const Geo& g, float gps0, float gps1, float* gxc, float* gyc) {
+  *gxc = rintf((g.cmax - gps0) / g.cell);
+  *gyc = rintf((gps1 - g.cmin) / g.cell);
+}
+
+// ---------------------------------------------------------------- unprojection
+// ComputeSpatialLocs.forward + validity/bounds of ProjectToGroundPlane.forward
+// (rgb_mapping.py:159-176, 188-204) for sampled pixel (i,j) of the Hf x Wf frame.
+// Returns true when the pixel writes; *x,*y are the ego cell.
+WSMG_HD bool unproject_pixel(const Geo& g, const float* depth_b, int i, int j, int* x, int* y) {
+  int r = (int)((float)i * g.ksub);
+  int c = (int)((float)j * g.ksub);
+  float z = depth_b[(size_t)r * g.Wd + c] * 10.0f;           // rgb_mapping.py:37
+  float xx = ((float)c - g.cx) / g.fx;
+  float yy = ((float)(g.Hd - r) - g.cy) / g.fy;
+  float X = xx * z, Y = yy * z;
+  bool ok = (z != 0.0f) && (Y > -1.5f) && (Y < 0.1f);
+  float xf = rintf(X / g.cell + g.half);
+  float yf = rintf(-(z / g.cell) + g.half);
+  ok = ok && (xf >= 0.0f) && (xf < (float)g.E) && (yf >= 0.0f) && (yf < (float)g.E);
+  *x = ok ? (int)xf : 0;
+  *y = ok ? (int)yf : 0;
+  return ok;
+}
+
+}  // namespace wsmg

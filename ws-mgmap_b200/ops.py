@@ -1,0 +1,113 @@
+"""Thin torch-tensor wrappers over the C ABI (include/wsmg.h).  Each function validates
+nothing beyond what it needs to build the call -- libwsmg validates dims/pointers and the
+error code is raised as WsmgError.  All work is enqueued on the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def dims_for(feat_shape, depth_shape, n_maps, e=100, g=240, resolution=0.12):
+    bs, c, hf, wf = feat_shape
+    return _lib.make_dims(bs, n_maps, c, hf, wf, depth_shape[1], depth_shape[2], e, g, resolution)
+
+
+def scratch_bytes(dims) -> int:
+    return int(_lib.load().wsmg_scratch_bytes(ctypes.byref(dims)))
+
+
+def alloc_scratch(dims, device):
+    n = scratch_bytes(dims)
+    if n == 0:
+        raise _lib.WsmgError("unsupported geometry for libwsmg (see include/wsmg.h WSMG_E_*)")
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, trig=None, scratch=None, ego=None):
+    """One step.  feat [bs,C,Hf,Wf], depth [bs,Hd,Wd,1], gmap [n,G,G,C] (updated in place).  Returns ego [bs,C,E,E]."""
+    lib = _lib.load()
+    dev = gmap.device
+    d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution)
+    if scratch is None:
+        scratch = alloc_scratch(d, dev)
+    if ego is None:
+        ego = torch.empty(feat.shape[0], feat.shape[1], e, e, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.wsmg_map_update(_ptr(feat), _ptr(depth), _ptr(gps), _ptr(compass), _ptr(mask), _ptr(gmap), _ptr(ego),
+                                 _ptr(trig), _ptr(scratch), scratch.numel(), ctypes.byref(d), _stream(dev))
+    _lib.check(rc, "wsmg_map_update")
+    return ego
+
+
+def unproject_index(depth, hf, wf, e=100, g=240, resolution=0.12):
+    """depth [bs,Hd,Wd,1] -> (lin int32 [bs,hf,wf], invalid bool [bs,hf,wf])."""
+    lib = _lib.load()
+    dev = depth.device
+    bs = depth.shape[0]
+    d = _lib.make_dims(bs, bs, 4, hf, wf, depth.shape[1], depth.shape[2], e, g, resolution)
+    lin = torch.empty(bs, hf, wf, dtype=torch.int32, device=dev)
+    inv = torch.empty(bs, hf, wf, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.wsmg_unproject_index(_ptr(depth), _ptr(lin), _ptr(inv), ctypes.byref(d), _stream(dev))
+    _lib.check(rc, "wsmg_unproject_index")
+    return lin, inv.bool()
+
+
+def scatter_max(feat, depth, e=100, g=240, resolution=0.12):
+    """-> proj_feats [bs,C,E,E] (before rotation)."""
+    lib = _lib.load()
+    dev = feat.device
+    d = dims_for(feat.shape, depth.shape, feat.shape[0], e, g, resolution)
+    scratch = alloc_scratch(d, dev)
+    proj = torch.empty(feat.shape[0], feat.shape[1], e, e, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.wsmg_scatter_max(_ptr(feat), _ptr(depth), _ptr(proj), _ptr(scratch), scratch.numel(),
+                                  ctypes.byref(d), _stream(dev))
+    _lib.check(rc, "wsmg_scatter_max")
+    return proj
+
+
+def register_fuse_retrieve(proj, gps, compass, mask, gmap, resolution=0.12, trig=None):
+    lib = _lib.load()
+    dev = gmap.device
+    bs, c, e, _ = proj.shape
+    d = _lib.make_dims(bs, gmap.shape[0], c, 4, 4, 4, 4, e, gmap.shape[1], resolution)
+    ego = torch.empty(bs, c, e, e, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.wsmg_register_fuse_retrieve(_ptr(proj), _ptr(gps), _ptr(compass), _ptr(mask), _ptr(gmap), _ptr(ego),
+                                             _ptr(trig), ctypes.byref(d), _stream(dev))
+    _lib.check(rc, "wsmg_register_fuse_retrieve")
+    return ego
+
+
+class HostPipeline:
+    """End-to-end step from HOST (pinned) buffers: H2D of the frame, update, D2H of the ego map,
+    chunked so copies overlap the kernels (wsmg_map_update_host)."""
+
+    def __init__(self, dims, device, chunk_envs=32):
+        self.lib = _lib.load()
+        self.dims = dims
+        self.device = torch.device(device)
+        self.chunk = int(min(chunk_envs, dims.bs))
+        n = int(self.lib.wsmg_host_staging_bytes(ctypes.byref(dims), self.chunk))
+        if n == 0:
+            raise _lib.WsmgError("unsupported geometry for libwsmg")
+        self.staging = torch.empty(n, dtype=torch.uint8, device=self.device)
+
+    def step(self, feat_h, depth_h, gps_h, compass_h, mask_h, gmap, ego_h):
+        with torch.cuda.device(self.device):
+            rc = self.lib.wsmg_map_update_host(_ptr(feat_h), _ptr(depth_h), _ptr(gps_h), _ptr(compass_h), _ptr(mask_h),
+                                               _ptr(gmap), _ptr(ego_h), _ptr(self.staging), self.staging.numel(),
+                                               self.chunk, ctypes.byref(self.dims), _stream(self.device))
+        _lib.check(rc, "wsmg_map_update_host")

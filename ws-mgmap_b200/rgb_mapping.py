@@ -1,0 +1,168 @@
+"""Drop-in for the reference's vlnce_baselines/common/rgb_mapping.py.
+
+Same names, constructor argument, call signature, tensor layouts and externally
+mutated state as the reference module, so `MGMapNet`
+(mg_map_policy.py:66,186), `BasePolicy.update_map` (policy.py:30-32) and the trainers'
+state juggling (common_trainer.py:142-187,266-267,428-435,454-476; dagger_trainer.py:322-327,
+668-678) keep working unchanged:
+
+    from wsmgmap_b200.rgb_mapping import RGBMapping, get_grid
+
+The per-step work is done by libwsmg.so (hand-written sm_100a kernels, C ABI in
+include/wsmg.h) on the caller's current CUDA stream.  There is no CPU or eager fallback:
+without a CUDA device or the built library the module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+
+class to_grid():
+    """GPS (metres) -> global-map cell, rgb_mapping.py:93-103 of the reference."""
+
+    def __init__(self, global_map_size, coordinate_min, coordinate_max):
+        self.global_map_size = global_map_size
+        self.coordinate_min = coordinate_min
+        self.coordinate_max = coordinate_max
+        self.grid_size = (coordinate_max - coordinate_min) / global_map_size
+
+    def get_grid_coords(self, positions):
+        col = positions[:, 0]
+        row = positions[:, 1]
+        return ((self.coordinate_max - col) / self.grid_size).round(), ((row - self.coordinate_min) / self.grid_size).round()
+
+
+def get_grid(pose, grid_size, device):
+    """Rotation and translation sampling grids for `pose` = (x, y, theta) per row.
+
+    Kept for habitat_extensions/sensors.py:22,383-410 (CPU use inside env workers);
+    same contract as rgb_mapping.py:106-139: returns (rot_grid, trans_grid), each
+    [bs, grid_h, grid_w, 2], built with F.affine_grid on `device`.
+    """
+    pose = pose.float()
+    tx, ty, th = pose[:, 0], pose[:, 1], pose[:, 2]
+    n = pose.shape[0]
+    c, s = th.cos(), th.sin()
+    rot = torch.zeros(n, 2, 3, device=device)
+    rot[:, 0, 0] = c
+    rot[:, 0, 1] = -s
+    rot[:, 1, 0] = s
+    rot[:, 1, 1] = c
+    trans = torch.zeros(n, 2, 3, device=device)
+    trans[:, 0, 0] = 1.0
+    trans[:, 1, 1] = 1.0
+    trans[:, 0, 2] = tx
+    trans[:, 1, 2] = ty
+    size = torch.Size(grid_size)
+    return F.affine_grid(rot, size, align_corners=False), F.affine_grid(trans, size, align_corners=False)
+
+
+class Mapping(nn.Module):
+    """State + geometry of the reference's Mapping (rgb_mapping.py:11-30).  Holds no
+    parameters and no registered buffers (the reference's state is plain attributes, so it
+    is absent from state_dict and DDP never touches it)."""
+
+    def __init__(self, model_config):
+        super().__init__()
+        self.device = torch.device("cuda", model_config.gpu_id)
+        self.num_proc = model_config.num_proc
+        self.resolution = model_config.resolution
+        self.egocentric_map_size = model_config.egocentric_map_size
+        self.global_map_size = model_config.global_map_size
+        self.global_map_depth = model_config.map_depth
+        coordinate_min = -self.global_map_size * self.resolution / 2
+        coordinate_max = self.global_map_size * self.resolution / 2
+        self.to_grid = to_grid(self.global_map_size, coordinate_min, coordinate_max)
+        if not torch.cuda.is_available():
+            raise RuntimeError("wsmgmap_b200.Mapping needs a CUDA device (no CPU fallback)")
+        self._lib = _lib.load()
+        g, c = self.global_map_size, self.global_map_depth
+        # caller-owned, re-bindable state: fetched from the attribute on every call
+        self.full_global_map = torch.zeros(self.num_proc, g, g, c, device=self.device)
+        self.agent_view = torch.zeros(self.num_proc, c, g, g, device=self.device)
+        self._scratch = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _dims(self, bs, n_maps, hf, wf, hd, wd):
+        return _lib.make_dims(bs, n_maps, self.global_map_depth, hf, wf, hd, wd,
+                              self.egocentric_map_size, self.global_map_size, self.resolution)
+
+    def _scratch_for(self, dims, device):
+        need = self._lib.wsmg_scratch_bytes(ctypes.byref(dims))
+        if need == 0:
+            raise _lib.WsmgError("unsupported geometry for libwsmg (see include/wsmg.h WSMG_E_*)")
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._scratch
+
+    @staticmethod
+    def _f32c(t, name, device):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a tensor")
+        if t.device != device:
+            raise ValueError(f"{name} is on {t.device}, the map lives on {device}")
+        if t.dtype != torch.float32:
+            t = t.float()
+        return t.contiguous()
+
+    # -- reference API ---------------------------------------------------------------------
+    def project_feat_to_map(self, features, full_global_map, observations, masks, _trig=None):
+        """rgb_mapping.py:32-72.  Updates `full_global_map[:bs]` in place and returns
+        (final_retrieval [bs,C,E,E], full_global_map)."""
+        if not full_global_map.is_cuda:
+            raise ValueError("full_global_map must be a CUDA tensor")
+        dev = full_global_map.device
+        if full_global_map.dtype != torch.float32 or not full_global_map.is_contiguous():
+            raise ValueError("full_global_map must be a contiguous fp32 [n,G,G,C] tensor")
+        g, c, e = self.global_map_size, self.global_map_depth, self.egocentric_map_size
+        if tuple(full_global_map.shape[1:]) != (g, g, c):
+            raise ValueError(f"full_global_map has shape {tuple(full_global_map.shape)}, expected [n,{g},{g},{c}]")
+        features = self._f32c(features, "features", dev)
+        bs, cf, hf, wf = features.shape
+        if cf != c:
+            raise ValueError(f"features have {cf} channels, map_depth is {c}")
+        if bs > full_global_map.shape[0]:
+            raise ValueError(f"batch {bs} larger than the map state ({full_global_map.shape[0]} envs)")
+        depth = self._f32c(observations["depth"], "observations['depth']", dev)
+        if depth.dim() != 4 or depth.shape[0] != bs or depth.shape[3] != 1:
+            raise ValueError("observations['depth'] must be [bs,Hd,Wd,1]")
+        gps = self._f32c(observations["gps"], "observations['gps']", dev)
+        compass = self._f32c(observations["compass"], "observations['compass']", dev)
+        masks = self._f32c(masks, "masks", dev)
+        if gps.shape != (bs, 2) or compass.numel() != bs or masks.numel() != bs:
+            raise ValueError("gps must be [bs,2], compass [bs,1], masks [bs,1]")
+        dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2])
+        scratch = self._scratch_for(dims, dev)
+        ego = ops.map_update(features, depth, gps, compass, masks, full_global_map, e=e, resolution=self.resolution,
+                             trig=_trig, scratch=scratch)
+        return ego, full_global_map
+
+
+class RGBMapping(Mapping):
+    def __init__(self, model_config):
+        super().__init__(model_config)
+
+    def forward(self, rgb_features, observations, masks):
+        """rgb_mapping.py:79-90: returns the cached ego map when the observations already carry
+        one (LMDB replay, unet_encoder.py:65-66); otherwise one map update."""
+        if 'rgb_ego_map' not in observations:
+            c_in = rgb_features.shape[1]
+            if c_in != self.global_map_depth:
+                # channel re-binning of rgb_mapping.py:82-84 (identity when C_in == map_depth, the shipped config)
+                bs, _, h, w = rgb_features.shape
+                x = rgb_features.permute(0, 2, 3, 1).reshape(bs, -1, c_in)
+                x = F.adaptive_max_pool1d(x, self.global_map_depth)
+                rgb_features = x.reshape(bs, h, w, -1).permute(0, 3, 1, 2)
+            final_retrieval, self.full_global_map = self.project_feat_to_map(
+                rgb_features, self.full_global_map, observations, masks)
+            observations['rgb_ego_map'] = final_retrieval
+        else:
+            final_retrieval = observations['rgb_ego_map']
+        return final_retrieval
