@@ -8,6 +8,7 @@
 //             (rgb_mapping.py:210-232, 37-70).  Body in wsmg_body.h.
 // No tensor cores: the path is gather / scatter-max / bilinear streaming (~0.3 flop/byte).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "wsmg_body.h"
 #include "wsmg_host.h"
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
 }
 
 // ------------------------------------------------------------------ k_fused
-template <bool VEC>
+template <int CE, int CG, bool VEC>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  fused_body<VEC>(p, blockIdx.x, smem, threadIdx.x, blockDim.x);
+  fused_body<CE, CG, VEC>(p, blockIdx.x, smem, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------ host glue
@@ -103,26 +104,29 @@ static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8
   return (int)cudaGetLastError();
 }
 
-static int launch_fused(const FusedParams& p, cudaStream_t s) {
-  const SmemPlan sp = make_plan(p.g);
+template <int CE, int CG, bool VEC>
+static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+  if (e != cudaSuccess) return (int)e;
+  k_fused<CE, CG, VEC><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// WSMG_FORCE_GENERIC=1 routes the reference geometry through the runtime-geometry kernel (tests).
+static int launch_fused(FusedParams p, cudaStream_t s) {
+  p.sp = make_plan(p.g);
   int dev = 0, max_optin = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
   e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (e != cudaSuccess) return (int)e;
-  if (sp.total > max_optin) return WSMG_E_SMEM;
+  if (p.sp.total > max_optin) return WSMG_E_SMEM;
   const bool vec = (p.g.C % 4) == 0;
-  const int slabs = (p.g.C + SLAB - 1) / SLAB;
-  if (vec) {
-    e = cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total);
-    if (e != cudaSuccess) return (int)e;
-    k_fused<true><<<p.bs * slabs, FUSED_THREADS, sp.total, s>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total);
-    if (e != cudaSuccess) return (int)e;
-    k_fused<false><<<p.bs * slabs, FUSED_THREADS, sp.total, s>>>(p);
-  }
-  return (int)cudaGetLastError();
+  const int grid = p.bs * ((p.g.C + SLAB - 1) / SLAB);
+  const char* force = getenv("WSMG_FORCE_GENERIC");
+  if (vec && p.g.E == 100 && p.g.G == 240 && !(force && force[0] == '1')) return launch_fused_t<100, 240, true>(p, grid, s);
+  if (vec) return launch_fused_t<0, 0, true>(p, grid, s);
+  return launch_fused_t<0, 0, false>(p, grid, s);
 }
 
 }  // namespace wsmg

@@ -4,12 +4,21 @@
 //     tests compare against the oracle.  The emulation is test infrastructure; nothing
 //     in the product path calls it.
 //
-// Shared-memory plan (E=100, G=240: 231.6 KB of the 227 KB... see fused_smem_bytes):
-//   X    [E*E] F4     rotated ego grid R, later the back-translated crop B
-//   P    planar u32 keys [4][fan_cells] during the scatter, then F4[fan_cells];
+// The kernel is instruction-issue bound before it is HBM bound (ncu, profiles/), so the
+// code below trades shared-memory tables for instructions everywhere:
+//   * every bilinear tap is `table lookup -> add -> max(.,0) -> LDS.128`; index 0 of X, of
+//     the fan and of the F ring is a zero cell that out-of-range taps resolve to;
+//   * the thread -> window-cell mapping of the fuse bands is fixed, so the loop carries only
+//     a pointer increment;
+//   * the reference geometry (E=100, G=240) is a template instantiation, divisions by E and
+//     E+2 become multiplies.
+//
+// Shared-memory plan (E=100, G=240: 230.7 KB of the 227 KiB an sm_100 CTA may opt in to):
+//   X    [1 + E*E] F4    zero cell + rotated ego grid R, later the back-translated crop B
+//   P    planar u32 keys [4][npp] during the scatter, then F4[1 + fan_cells] (zero cell first);
 //        after the first rotation the region is reused for the F ring + translate tables
 //   Gst  2 x [BAND*WW] F4   cp.async-staged bands of the caller's global map window
-//   tail baseE[E], rowoff[fan_rows], flags
+//   tail baseE[E], fanrow[E+1], flags
 #pragma once
 #include "wsmg_math.h"
 
@@ -26,9 +35,55 @@ namespace wsmg {
 constexpr int SLAB = 4;     // channels per CTA
 constexpr int BAND = 8;     // window rows per fuse band
 constexpr int RING = BAND + 2;
+constexpr int NEG = -(1 << 24);   // "tap out of range": any index sum containing it is negative
 
 struct alignas(16) F4 { float v[4]; };
+struct alignas(16) I4 { int a, b, c, d; };
+struct alignas(8) I2 { int a, b; };
 WSMG_HD F4 f4_zero() { F4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0f; return r; }
+WSMG_HD float as_float(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float f; __builtin_memcpy(&f, &i, 4); return f;
+#endif
+}
+WSMG_HD int as_int(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i; __builtin_memcpy(&i, &f, 4); return i;
+#endif
+}
+WSMG_HD int imax0(int a) { return a > 0 ? a : 0; }
+
+struct SmemPlan {
+  int x_off, p_off, p_bytes, gst_off, base_off, fanrow_off, flag_off, total;
+  int npp;                 // words per key plane during the scatter
+  int ring_off, tab_off;   // views inside the P region after the first rotation
+};
+
+WSMG_HD int align16(int x) { return (x + 15) & ~15; }
+
+WSMG_HD SmemPlan make_plan(const Geo& g) {
+  SmemPlan s;
+  const int WW = g.E + 2;
+  s.npp = (g.fan_cells + 1 + 3) & ~3;
+  s.x_off = 0;
+  s.p_off = align16((1 + g.E * g.E) * 16);
+  int p_scatter = s.npp * 16;
+  int ring_bytes = (1 + RING * WW) * 16;
+  int tab_bytes = (2 * WW + 2 * g.E) * 16;
+  s.ring_off = s.p_off;
+  s.tab_off = s.p_off + ring_bytes;
+  s.p_bytes = p_scatter > ring_bytes + tab_bytes ? p_scatter : ring_bytes + tab_bytes;
+  s.gst_off = s.p_off + align16(s.p_bytes);
+  s.base_off = s.gst_off + 2 * BAND * WW * 16;
+  s.fanrow_off = s.base_off + align16(g.E * 4);
+  s.flag_off = s.fanrow_off + align16((g.E + 1) * 8);
+  s.total = s.flag_off + 16;
+  return s;
+}
 
 struct FusedParams {
   const float* feat;        // [bs,C,Hf,Wf]
@@ -43,36 +98,8 @@ struct FusedParams {
   int stop_after_scatter;   // stage API: return after writing proj_out
   int bs;
   Geo g;
+  SmemPlan sp;
 };
-
-struct SmemPlan {
-  int x_off, p_off, p_bytes, gst_off, base_off, rowoff_off, flag_off, total;
-  int npp;       // padded cells per key plane
-  // views inside the P region after the first rotation
-  int ring_off, tab_off;
-};
-
-WSMG_HD int align16(int x) { return (x + 15) & ~15; }
-
-WSMG_HD SmemPlan make_plan(const Geo& g) {
-  SmemPlan s;
-  const int WW = g.E + 2;
-  s.npp = (g.fan_cells + 3) & ~3;
-  s.x_off = 0;
-  s.p_off = align16(g.E * g.E * 16);
-  int p_scatter = s.npp * 16;
-  int ring_bytes = RING * WW * 16;
-  int tab_bytes = align16((4 * WW + 4 * g.E) * 4);
-  s.ring_off = s.p_off;
-  s.tab_off = s.p_off + ring_bytes;
-  s.p_bytes = p_scatter > ring_bytes + tab_bytes ? p_scatter : ring_bytes + tab_bytes;
-  s.gst_off = s.p_off + align16(s.p_bytes);
-  s.base_off = s.gst_off + 2 * BAND * WW * 16;
-  s.rowoff_off = s.base_off + align16(g.E * 4);
-  s.flag_off = s.rowoff_off + align16((g.fan_rows + 1) * 4);
-  s.total = s.flag_off + 16;
-  return s;
-}
 
 // ------------------------------------------------------------------ platform shims
 #if defined(__CUDACC__)
@@ -81,6 +108,7 @@ __device__ __forceinline__ F4 ld_stream4(const float* p) {
   float4 t = __ldcs(reinterpret_cast<const float4*>(p));
   F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
 }
+__device__ __forceinline__ uint2 ld_codes(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void async_copy16(void* dst_smem, const void* src, bool pred) {
   unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -99,6 +127,7 @@ template <int N> __device__ __forceinline__ void async_wait() {
 #else
 inline void smem_max(uint32_t* a, uint32_t v) { if (v > *a) *a = v; }
 inline F4 ld_stream4(const float* p) { F4 r; for (int i = 0; i < 4; ++i) r.v[i] = p[i]; return r; }
+inline uint2 ld_codes(const uint2* p) { return *p; }
 inline void st_stream(float* p, float v) { *p = v; }
 inline void async_copy16(void* dst, const void* src, bool pred) {
   if (pred) __builtin_memcpy(dst, src, 16); else __builtin_memset(dst, 0, 16);
@@ -110,46 +139,64 @@ inline void async_commit() {}
 template <int N> inline void async_wait() {}
 #endif
 
+WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const Weights& w) {
+  F4 r;
+#pragma unroll
+  for (int ch = 0; ch < SLAB; ++ch) r.v[ch] = blend4(a.v[ch], b.v[ch], c.v[ch], d.v[ch], w.nw, w.ne, w.sw, w.se);
+  return r;
+}
+
 // ------------------------------------------------------------------ the CTA body
+// CE/CG > 0: geometry known at compile time (the reference's 100/240); 0: read it from p.g.
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
-template <bool VEC>
+template <int CE, int CG, bool VEC>
 WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, int tid0, int ts) {
   const Geo& g = p.g;
-  const int E = g.E, G = g.G, C = g.C, WW = E + 2;
+  const int E = CE > 0 ? CE : g.E;
+  const int G = CG > 0 ? CG : g.G;
+  const int C = g.C, WW = E + 2, EE = E * E;
   const int HW = g.Hf * g.Wf;
   const int slabs = (C + SLAB - 1) / SLAB;
   const int b = block / slabs;
   const int c0 = (block - b * slabs) * SLAB;
   const int nch = (C - c0) < SLAB ? (C - c0) : SLAB;
-  const SmemPlan sp = make_plan(g);
+  const SmemPlan& sp = p.sp;
+  const int paste_lo = G / 2 - E / 2;
+  const float half_e = (float)E / 2.0f, half_g = (float)G / 2.0f, gcenter = (float)(G / 2);
 
-  F4* X = reinterpret_cast<F4*>(smem + sp.x_off);
+  F4* X = reinterpret_cast<F4*>(smem + sp.x_off);          // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
   uint32_t* Pk = reinterpret_cast<uint32_t*>(smem + sp.p_off);
-  F4* Pf = reinterpret_cast<F4*>(smem + sp.p_off);
+  F4* Pf = reinterpret_cast<F4*>(smem + sp.p_off);         // Pf[0] = zero cell, fan cell c at Pf[1 + c]
   F4* Gst = reinterpret_cast<F4*>(smem + sp.gst_off);
   float* baseE = reinterpret_cast<float*>(smem + sp.base_off);
-  int* rowoff = reinterpret_cast<int*>(smem + sp.rowoff_off);
+  I2* fanrow = reinterpret_cast<I2*>(smem + sp.fanrow_off); // per grid row y (entry E = "no such row"): {1+rowoff-xs, xs | xe<<16}
   int* flags = reinterpret_cast<int*>(smem + sp.flag_off);
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63
-  float gxc, gyc;
-  gps_cell(g, p.gps[2 * b], p.gps[2 * b + 1], &gxc, &gyc);
-  float sy = gxc - g.gcenter, sx = gyc - g.gcenter;
-  const float qx = sx / g.gcenter, qy = sy / g.gcenter;     // retrieval pose; forward pose is the negation
-  const float lim = (float)(4 * G);
-  sy = fminf(fmaxf(sy, -lim), lim);                         // far-out (or NaN) poses: window leaves the map
-  sx = fminf(fmaxf(sx, -lim), lim);
-  const int u0 = (int)sy + g.paste_lo - 1;                  // global row / col of window cell (0,0)
-  const int v0 = (int)sx + g.paste_lo - 1;
-  float* gmap_b = p.gmap + (size_t)b * G * G * C;
+  float qx = 0.f, qy = 0.f;
+  int u0 = 0, v0 = 0;
+  float* gmap_b = nullptr;
+  if (!p.stop_after_scatter) {
+    float gxc, gyc;
+    gps_cell(g, p.gps[2 * b], p.gps[2 * b + 1], &gxc, &gyc);
+    float sy = gxc - gcenter, sx = gyc - gcenter;
+    qx = sx / gcenter; qy = sy / gcenter;                   // retrieval pose; the forward pose is its negation
+    const float lim = (float)(4 * G);
+    sy = fminf(fmaxf(sy, -lim), lim);                       // far-out (or NaN) poses: the window leaves the map
+    sx = fminf(fmaxf(sx, -lim), lim);
+    u0 = (int)sy + paste_lo - 1;                            // global row / col of window cell (0,0)
+    v0 = (int)sx + paste_lo - 1;
+    gmap_b = p.gmap + (size_t)b * G * G * C + c0;
+  }
 
+  // cp.async one band of the caller's map window into Gst[k&1]; cells outside the map are zero-filled
   auto prefetch_band = [&](int k) {
     F4* dst = Gst + (k & 1) * BAND * WW;
     for (int t = tid0; t < BAND * WW; t += ts) {
       int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
       int u = u0 + uu, v = v0 + vv;
-      bool inside = uu < WW && u >= 0 && u < G && v >= 0 && v < G;
-      const float* src = gmap_b + ((size_t)(inside ? u : 0) * G + (inside ? v : 0)) * C + c0;
+      bool inside = uu < WW && (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
+      const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
       if (VEC) {
         async_copy16(dst + t, src, inside);
       } else {
@@ -166,12 +213,17 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 
   // ---- tables ------------------------------------------------------------------------------
   for (int t = tid0; t < E; t += ts) baseE[t] = base_coord(t, E);
-  for (int t = tid0; t <= g.fan_rows; t += ts) {
-    int off = 0;
-    for (int y = 0; y < t; ++y) off += fan_row_width(y, E);
-    rowoff[t] = off;
+  for (int t = tid0; t <= E; t += ts) {
+    I2 fr; fr.a = 0; fr.b = 1;                              // xs = 1 > xe = 0: empty row
+    if (t < g.fan_rows) {
+      int off = 0;
+      for (int y = 0; y < t; ++y) off += fan_row_width(y, E);
+      int xs = fan_x_lo(t), xe = fan_x_hi(t, E);
+      fr.a = 1 + off - xs; fr.b = xs | (xe << 16);
+    }
+    fanrow[t] = fr;
   }
-  if (tid0 == 0) flags[0] = 0;
+  if (tid0 == 0) { flags[0] = 0; X[0] = f4_zero(); }
   for (int t = tid0; t < SLAB * sp.npp; t += ts) Pk[t] = 0u;
   WSMG_SYNC();
 
@@ -189,47 +241,44 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         int tt = t + h * ts;
-        live[h] = tt < n4;
         cc[h].x = cc[h].y = 0xFFFFFFFFu;
-        if (live[h]) {
-#if defined(__CUDACC__)
-          cc[h] = __ldg(codes4 + tt);
-#else
-          cc[h] = codes4[tt];
-#endif
-        }
+        if (tt < n4) cc[h] = ld_codes(codes4 + tt);
       }
+      uint32_t code[2][4];
+      bool ok[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         int tt = t + h * ts;
-        // packed codes of valid pixels are < CODE_OUTLIER; skip the feature read when none of the four writes
-        bool any = live[h] && (((cc[h].x & 0xFFFFu) < CODE_OUTLIER) || ((cc[h].x >> 16) < CODE_OUTLIER) ||
-                               ((cc[h].y & 0xFFFFu) < CODE_OUTLIER) || ((cc[h].y >> 16) < CODE_OUTLIER));
-        live[h] = any;
+        code[h][0] = cc[h].x & 0xFFFFu; code[h][1] = cc[h].x >> 16;
+        code[h][2] = cc[h].y & 0xFFFFu; code[h][3] = cc[h].y >> 16;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) ok[h][px] = code[h][px] < CODE_OUTLIER;   // valid pixels carry a fan cell
+        const bool any_ok = ok[h][0] || ok[h][1] || ok[h][2] || ok[h][3];
+        const bool all_ok = ok[h][0] && ok[h][1] && ok[h][2] && ok[h][3];
+        if (tt < n4 && !all_ok) saw_invalid = 1;
+        live[h] = tt < n4 && any_ok;                 // a group where no pixel writes skips its feature read
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
-          if (any && ch < nch) f[h][ch] = ld_stream4(plane0 + (size_t)ch * HW + 4 * (size_t)tt);
+          if (live[h] && ch < nch) f[h][ch] = ld_stream4(plane0 + (size_t)ch * HW + 4 * (size_t)tt);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t code[5];
-        code[0] = cc[h].x & 0xFFFFu; code[1] = cc[h].x >> 16;
-        code[2] = cc[h].y & 0xFFFFu; code[3] = cc[h].y >> 16; code[4] = 0xFFFFFFFFu;
-        if ((t + h * ts) < n4 &&
-            (code[0] >= CODE_OUTLIER || code[1] >= CODE_OUTLIER || code[2] >= CODE_OUTLIER || code[3] >= CODE_OUTLIER))
-          saw_invalid = 1;
         if (!live[h]) continue;
+        bool last[4];
+        last[0] = code[h][1] != code[h][0]; last[1] = code[h][2] != code[h][1];
+        last[2] = code[h][3] != code[h][2]; last[3] = true;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch) {
           if (ch >= nch) break;
           uint32_t* plane = Pk + ch * sp.npp;
-          uint32_t run = 0u;
+          // runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
+          // finish_cell() turns -0 into +0 like the reference), one shared-memory atomic per run
+          float run = -INFINITY;
 #pragma unroll
           for (int px = 0; px < 4; ++px) {
-            if (code[px] < CODE_OUTLIER) {
-              uint32_t k = f2key(f[h][ch].v[px]);
-              run = k > run ? k : run;
-              if (code[px + 1] != code[px]) { smem_max(plane + code[px], run); run = 0u; }
+            if (ok[h][px]) {
+              run = fmaxf(run, f[h][ch].v[px]);
+              if (last[px]) { smem_max(plane + code[h][px], f2key(run)); run = -INFINITY; }
             }
           }
         }
@@ -251,40 +300,42 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         if (t == 0 && inv && k < sentinel_key) k = sentinel_key;   // invalid pixels write -1e16 to cell 0 (:207-212)
         v.v[ch] = ch < nch ? finish_cell(k) : 0.0f;
       }
-      X[t] = v;
+      X[1 + t] = v;
     }
     WSMG_SYNC();
-    for (int t = tid0; t < g.fan_cells; t += ts) Pf[t] = X[t];
+    for (int t = tid0; t < g.fan_cells; t += ts) Pf[1 + t] = X[1 + t];
+    if (tid0 == 0) Pf[0] = f4_zero();
   } else {
     // stage API: load the projection (zero outside the fan by construction)
-    const float* src = p.proj_in + ((size_t)b * C + c0) * E * E;
+    const float* src = p.proj_in + ((size_t)b * C + c0) * EE;
     for (int y = 0; y < g.fan_rows; ++y) {
       int xs = fan_x_lo(y), w = fan_row_width(y, E);
+      int base = fanrow[y].a + xs;
       for (int t = tid0; t < w; t += ts) {
         F4 v;
 #pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch) v.v[ch] = ch < nch ? src[(size_t)ch * E * E + y * E + xs + t] : 0.0f;
-        Pf[rowoff[y] + t] = v;
+        for (int ch = 0; ch < SLAB; ++ch) v.v[ch] = ch < nch ? src[(size_t)ch * EE + y * E + xs + t] : 0.0f;
+        Pf[base + t] = v;
       }
     }
+    if (tid0 == 0) Pf[0] = f4_zero();
   }
   WSMG_SYNC();
 
-  auto fan_at = [&](int y, int x) -> F4 {
-    if (y < 0 || y >= g.fan_rows) return f4_zero();
-    int xs = fan_x_lo(y);
-    if (x < xs || x > fan_x_hi(y, E)) return f4_zero();
-    return Pf[rowoff[y] + x - xs];
+  // fan tap: row info -> index (0 = zero cell when the row or the column is outside the fan)
+  auto fan_idx = [&](const I2 fr, int x) -> int {
+    int xs = fr.b & 0xFFFF, xe = fr.b >> 16;
+    return (x >= xs && x <= xe) ? fr.a + x : 0;
   };
 
   if (p.proj_out != nullptr) {
-    float* dst = p.proj_out + ((size_t)b * C + c0) * E * E;
-    for (int t = tid0; t < E * E; t += ts) {
+    float* dst = p.proj_out + ((size_t)b * C + c0) * EE;
+    for (int t = tid0; t < EE; t += ts) {
       int y = t / E, x = t - y * E;
-      F4 v = fan_at(y, x);
+      F4 v = Pf[fan_idx(fanrow[y], x)];
 #pragma unroll
       for (int ch = 0; ch < SLAB; ++ch)
-        if (ch < nch) dst[(size_t)ch * E * E + t] = v.v[ch];
+        if (ch < nch) dst[(size_t)ch * EE + t] = v.v[ch];
     }
   }
   if (p.stop_after_scatter) return;
@@ -293,59 +344,68 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float cs, sn;
   if (p.trig != nullptr) { cs = p.trig[4 * b + 0]; sn = p.trig[4 * b + 1]; }
   else { float h = -p.compass[b]; sn = sinf(h); cs = cosf(h); }
-  for (int t = tid0; t < E * E; t += ts) {
+  for (int t = tid0; t < EE; t += ts) {
     int i = t / E, j = t - i * E;
     float ix, iy;
-    rot_coords(baseE[j], baseE[i], cs, sn, g.half_e, &ix, &iy);
+    rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
     Tap1D tx = make_tap(ix), ty = make_tap(iy);
     Weights w = make_weights(tx.w1, ty.w1);
-    F4 a = fan_at(ty.i0, tx.i0), bb = fan_at(ty.i0, tx.i0 + 1);
-    F4 c = fan_at(ty.i0 + 1, tx.i0), d = fan_at(ty.i0 + 1, tx.i0 + 1);
-    F4 r;
-#pragma unroll
-    for (int ch = 0; ch < SLAB; ++ch) r.v[ch] = blend4(a.v[ch], bb.v[ch], c.v[ch], d.v[ch], w.nw, w.ne, w.sw, w.se);
-    X[t] = r;
+    int y0 = ty.i0, y1 = ty.i0 + 1;
+    I2 r0 = fanrow[(unsigned)y0 < (unsigned)E ? y0 : E];
+    I2 r1 = fanrow[(unsigned)y1 < (unsigned)E ? y1 : E];
+    F4 a = Pf[fan_idx(r0, tx.i0)], bb = Pf[fan_idx(r0, tx.i0 + 1)];
+    F4 c = Pf[fan_idx(r1, tx.i0)], d = Pf[fan_idx(r1, tx.i0 + 1)];
+    X[1 + t] = blend_f4(a, bb, c, d, w);
   }
   WSMG_SYNC();
 
   // ---- phase 3 tables: the two (separable) translations (rgb_mapping.py:45-53, 57-65) ----------
-  int* colX0 = reinterpret_cast<int*>(smem + sp.tab_off);
-  float* colW = reinterpret_cast<float*>(colX0 + WW);
-  int* rowY0 = reinterpret_cast<int*>(colW + WW);
-  float* rowW = reinterpret_cast<float*>(rowY0 + WW);
-  int* bX0 = reinterpret_cast<int*>(rowW + WW);
-  float* bWx = reinterpret_cast<float*>(bX0 + E);
-  int* bY0 = reinterpret_cast<int*>(bWx + E);
-  float* bWy = reinterpret_cast<float*>(bY0 + E);
-  F4* ring = reinterpret_cast<F4*>(smem + sp.ring_off);
+  // colT[vv] = {x0 or NEG, x0+1 or NEG, bits(wx), inside};   rowT[uu] = {1 + y0*E or NEG, 1 + (y0+1)*E or NEG, bits(wy), inside}
+  // bXT[q]   = {col0 or NEG, col1 or NEG, bits(wx), 0};      bYT[p]   = {1 + slot(row0)*WW or NEG, 1 + slot(row1)*WW or NEG, bits(wy), 0}
+  I4* colT = reinterpret_cast<I4*>(smem + sp.tab_off);
+  I4* rowT = colT + WW;
+  I4* bXT = rowT + WW;
+  I4* bYT = bXT + E;
+  F4* ring = reinterpret_cast<F4*>(smem + sp.ring_off);     // ring[0] = zero cell
   for (int t = tid0; t < WW; t += ts) {
     int v = v0 + t, u = u0 + t;
-    if (v >= 0 && v < G) {        // canvas column sampled by global column v, relative to the pasted ego grid
-      Tap1D tp = make_tap(unnormalize(base_coord(v, G) + (-qx), g.half_g));
-      colX0[t] = tp.i0 - g.paste_lo; colW[t] = tp.w1;
-    } else { colX0[t] = -4; colW[t] = 0.0f; }
-    if (u >= 0 && u < G) {
-      Tap1D tp = make_tap(unnormalize(base_coord(u, G) + (-qy), g.half_g));
-      rowY0[t] = tp.i0 - g.paste_lo; rowW[t] = tp.w1;
-    } else { rowY0[t] = -4; rowW[t] = 0.0f; }
+    I4 ct; ct.a = ct.b = NEG; ct.c = 0; ct.d = 0;
+    if ((unsigned)v < (unsigned)G) {    // canvas column sampled by global column v, relative to the pasted ego grid
+      Tap1D tp = make_tap(unnormalize(base_coord(v, G) + (-qx), half_g));
+      int x0 = tp.i0 - paste_lo;
+      ct.a = (unsigned)x0 < (unsigned)E ? x0 : NEG;
+      ct.b = (unsigned)(x0 + 1) < (unsigned)E ? x0 + 1 : NEG;
+      ct.c = as_int(tp.w1); ct.d = 1;
+    }
+    colT[t] = ct;
+    I4 rt; rt.a = rt.b = NEG; rt.c = 0; rt.d = 0;
+    if ((unsigned)u < (unsigned)G) {
+      Tap1D tp = make_tap(unnormalize(base_coord(u, G) + (-qy), half_g));
+      int y0 = tp.i0 - paste_lo;
+      rt.a = (unsigned)y0 < (unsigned)E ? 1 + y0 * E : NEG;
+      rt.b = (unsigned)(y0 + 1) < (unsigned)E ? 1 + (y0 + 1) * E : NEG;
+      rt.c = as_int(tp.w1); rt.d = 1;
+    }
+    rowT[t] = rt;
   }
   for (int t = tid0; t < E; t += ts) {   // global column / row sampled by crop cell t, relative to the window
-    Tap1D tp = make_tap(unnormalize(base_coord(t + g.paste_lo, G) + qx, g.half_g));
-    bX0[t] = tp.i0 - v0; bWx[t] = tp.w1;
-    Tap1D tq = make_tap(unnormalize(base_coord(t + g.paste_lo, G) + qy, g.half_g));
-    bY0[t] = tq.i0 - u0; bWy[t] = tq.w1;
+    Tap1D tp = make_tap(unnormalize(base_coord(t + paste_lo, G) + qx, half_g));
+    int cx = tp.i0 - v0;
+    I4 bx; bx.a = (unsigned)cx < (unsigned)WW ? cx : NEG; bx.b = (unsigned)(cx + 1) < (unsigned)WW ? cx + 1 : NEG;
+    bx.c = as_int(tp.w1); bx.d = 0;
+    bXT[t] = bx;
+    Tap1D tq = make_tap(unnormalize(base_coord(t + paste_lo, G) + qy, half_g));
+    int ry = tq.i0 - u0;
+    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + (ry % RING) * WW : NEG;
+    by.b = (unsigned)(ry + 1) < (unsigned)WW ? 1 + ((ry + 1) % RING) * WW : NEG;
+    by.c = as_int(tq.w1); by.d = 0;
+    bYT[t] = by;
   }
-
-  auto rot_at = [&](int y, int x) -> F4 {
-    if (y < 0 || y >= E || x < 0 || x >= E) return f4_zero();
-    return X[y * E + x];
-  };
-  auto ring_at = [&](int row, int col) -> F4 {
-    if (row < 0 || row >= WW || col < 0 || col >= WW) return f4_zero();
-    return ring[(row % RING) * WW + col];
-  };
+  if (tid0 == 0) ring[0] = f4_zero();
+  WSMG_SYNC();
 
   // ---- phase 3: banded translate + max-fuse (:53-56) and translate back + crop (:64-69) -------
+  // BAND*WW and RING*E are below the CTA size: each loop below is one trip per thread and band.
   int p_lo = 0;
   for (int k = 0; k < NB; ++k) {
     if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
@@ -354,19 +414,16 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     for (int t = tid0; t < BAND * WW; t += ts) {
       int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
       if (uu >= WW) continue;
-      int u = u0 + uu, v = v0 + vv;
+      const I4 ct = colT[vv], rt = rowT[uu];
       F4 f = f4_zero();
-      if (u >= 0 && u < G && v >= 0 && v < G) {
-        int ry = rowY0[uu], rx = colX0[vv];
-        Weights w = make_weights(colW[vv], rowW[uu]);
-        F4 a = rot_at(ry, rx), bb = rot_at(ry, rx + 1), c = rot_at(ry + 1, rx), d = rot_at(ry + 1, rx + 1);
+      if (ct.d & rt.d) {
+        Weights w = make_weights(as_float(ct.c), as_float(rt.c));
+        F4 a = X[imax0(rt.a + ct.a)], bb = X[imax0(rt.a + ct.b)], c = X[imax0(rt.b + ct.a)], d = X[imax0(rt.b + ct.b)];
+        F4 tv = blend_f4(a, bb, c, d, w);
         F4 old = gst[t];
 #pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch) {
-          float tv = blend4(a.v[ch], bb.v[ch], c.v[ch], d.v[ch], w.nw, w.ne, w.sw, w.se);
-          f.v[ch] = fmaxf(old.v[ch], tv);
-        }
-        float* dst = gmap_b + ((size_t)u * G + v) * C + c0;
+        for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(old.v[ch], tv.v[ch]);
+        float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
         if (VEC) {
           *reinterpret_cast<F4*>(dst) = f;
         } else {
@@ -375,7 +432,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
             if (ch < nch) dst[ch] = f.v[ch];
         }
       }
-      ring[(uu % RING) * WW + vv] = f;
+      ring[1 + (uu % RING) * WW + vv] = f;
     }
     WSMG_SYNC();
     if (k + 2 < NB) prefetch_band(k + 2);
@@ -383,14 +440,11 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     int done = (k + 1) * BAND < WW ? (k + 1) * BAND : WW;
     int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
     for (int t = tid0; t < (p_hi - p_lo) * E; t += ts) {
-      int pr = p_lo + t / E, q = t % E;
-      int fy = bY0[pr], fx = bX0[q];
-      Weights w = make_weights(bWx[q], bWy[pr]);
-      F4 a = ring_at(fy, fx), bb = ring_at(fy, fx + 1), c = ring_at(fy + 1, fx), d = ring_at(fy + 1, fx + 1);
-      F4 r;
-#pragma unroll
-      for (int ch = 0; ch < SLAB; ++ch) r.v[ch] = blend4(a.v[ch], bb.v[ch], c.v[ch], d.v[ch], w.nw, w.ne, w.sw, w.se);
-      X[pr * E + q] = r;
+      int dr = t / E, q = t - dr * E, pr = p_lo + dr;
+      const I4 bx = bXT[q], by = bYT[pr];
+      Weights w = make_weights(as_float(bx.c), as_float(by.c));
+      F4 a = ring[imax0(by.a + bx.a)], bb = ring[imax0(by.a + bx.b)], c = ring[imax0(by.b + bx.a)], d = ring[imax0(by.b + bx.b)];
+      X[1 + pr * E + q] = blend_f4(a, bb, c, d, w);
     }
     p_lo = p_hi;
   }
@@ -399,18 +453,21 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // ---- phase 4: ego = rotate(B, +compass), NCHW out (rgb_mapping.py:70) ----------------------
   if (p.trig != nullptr) { cs = p.trig[4 * b + 2]; sn = p.trig[4 * b + 3]; }
   else { float h = p.compass[b]; sn = sinf(h); cs = cosf(h); }
-  float* ego_b = p.ego + ((size_t)b * C + c0) * E * E;
-  for (int t = tid0; t < E * E; t += ts) {
+  float* ego_b = p.ego + ((size_t)b * C + c0) * EE;
+  for (int t = tid0; t < EE; t += ts) {
     int i = t / E, j = t - i * E;
     float ix, iy;
-    rot_coords(baseE[j], baseE[i], cs, sn, g.half_e, &ix, &iy);
+    rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
     Tap1D tx = make_tap(ix), ty = make_tap(iy);
     Weights w = make_weights(tx.w1, ty.w1);
-    F4 a = rot_at(ty.i0, tx.i0), bb = rot_at(ty.i0, tx.i0 + 1);
-    F4 c = rot_at(ty.i0 + 1, tx.i0), d = rot_at(ty.i0 + 1, tx.i0 + 1);
+    int x0 = tx.i0, y0 = ty.i0;
+    int cx0 = (unsigned)x0 < (unsigned)E ? x0 : NEG, cx1 = (unsigned)(x0 + 1) < (unsigned)E ? x0 + 1 : NEG;
+    int ry0 = (unsigned)y0 < (unsigned)E ? 1 + y0 * E : NEG, ry1 = (unsigned)(y0 + 1) < (unsigned)E ? 1 + (y0 + 1) * E : NEG;
+    F4 a = X[imax0(ry0 + cx0)], bb = X[imax0(ry0 + cx1)], c = X[imax0(ry1 + cx0)], d = X[imax0(ry1 + cx1)];
+    F4 r = blend_f4(a, bb, c, d, w);
 #pragma unroll
     for (int ch = 0; ch < SLAB; ++ch)
-      if (ch < nch) st_stream(ego_b + (size_t)ch * E * E + t, blend4(a.v[ch], bb.v[ch], c.v[ch], d.v[ch], w.nw, w.ne, w.sw, w.se));
+      if (ch < nch) st_stream(ego_b + (size_t)ch * EE + t, r.v[ch]);
   }
 }
 

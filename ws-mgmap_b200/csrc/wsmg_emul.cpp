@@ -5,6 +5,7 @@
 // against the oracle without a GPU.  It cannot find races; the GPU parity tests do that.
 // Not linked into libwsmg.so and not reachable from the product API.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -52,6 +53,8 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
   const Geo g = make_geo(d);
   const SmemPlan sp = make_plan(g);
   const int HW = g.Hf * g.Wf;
+  const char* force = getenv("WSMG_FORCE_GENERIC");
+  const bool generic = force && force[0] == '1';
   std::vector<uint16_t> codes((size_t)d->bs * HW);
   if (mode != 2) wsmg_emul_unproject_index(depth, nullptr, nullptr, codes.data(), d);
   if (mode != 1) {
@@ -65,14 +68,15 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
   FusedParams p{};
   p.feat = feat; p.codes = codes.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
   p.ego = ego_out; p.proj_out = proj_out; p.proj_in = (mode == 2) ? proj_in : nullptr;
-  p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g;
+  p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g; p.sp = sp;
   std::vector<unsigned char> smem(sp.total + 16);
   unsigned char* sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
   const int slabs = (g.C + SLAB - 1) / SLAB;
   for (int blk = 0; blk < d->bs * slabs; ++blk) {
     memset(sm, 0xCD, sp.total);     // poison: nothing may rely on zeroed shared memory
-    if (g.C % 4 == 0) fused_body<true>(p, blk, sm, 0, 1);
-    else fused_body<false>(p, blk, sm, 0, 1);
+    if (g.C % 4 == 0 && g.E == 100 && g.G == 240 && !generic) fused_body<100, 240, true>(p, blk, sm, 0, 1);
+    else if (g.C % 4 == 0) fused_body<0, 0, true>(p, blk, sm, 0, 1);
+    else fused_body<0, 0, false>(p, blk, sm, 0, 1);
   }
   return 0;
 }
