@@ -6,7 +6,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.log
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; grep -E "^(E   |FAILED|ERROR)|passed|failed" $OUT/pytest_gpu.log | cut -c1-300 | tail -12
+[ -x scripts/microbench_atoms ] && { echo "== microbench atoms"; timeout 120 scripts/microbench_atoms | tee $OUT/microbench_atoms.log; }
 echo "== bench"; timeout 900 python bench.py 2>$OUT/bench.err | tee $OUT/bench.json; tail -3 $OUT/bench.err
 echo "== bench env8"; timeout 600 python bench.py --workload env8 --no-cpu-baseline 2>>$OUT/bench.err | tee $OUT/bench_env8.json
 if [ "$MODE" = "full" ]; then

@@ -86,6 +86,7 @@ def test_trajectory_100_steps_vs_oracle():
     resets = {b: 20 + 9 * b for b in range(bs)}
     kinds = ("uniform", "near", "room2", "room4")
     worst = 0.0
+    scale = 0.0            # the map keeps values of earlier frames: tolerances scale with the largest |feature| seen so far
     for t in range(steps):
         gps, compass, masks = walk.step()
         for b, when in resets.items():
@@ -109,11 +110,13 @@ def test_trajectory_100_steps_vs_oracle():
         assert torch.equal(ego.cpu(), want), f"step {t}: ego map (oracle trig)"
         assert torch.equal(gmap.cpu(), orc.full_global_map), f"step {t}: global map (oracle trig)"
         ego2 = ops.map_update(fd, dd, gps.to(DEV), compass.to(DEV), masks.to(DEV), gmap_dev_trig)
-        tol = 1e-5 * want.abs() + 2e-5 * feat.abs().max()
+        scale = max(scale, feat.abs().max().item())
+        tol = 1e-5 * want.abs() + 2e-5 * scale
         err = (ego2.cpu() - want).abs()
         assert (err <= tol).all(), f"step {t}: ego map (device trig) max err {err.max().item()}"
         gerr = (gmap_dev_trig.cpu() - orc.full_global_map).abs()
-        assert (gerr <= 1e-5 * orc.full_global_map.abs() + 2e-5 * feat.abs().max()).all(), f"step {t}: global map (device trig)"
+        gtol = 1e-5 * orc.full_global_map.abs() + 2e-5 * scale
+        assert (gerr <= gtol).all(), f"step {t}: global map (device trig) max err {gerr.max().item()} ratio {(gerr / gtol).max().item()}"
         worst = max(worst, err.max().item())
     print(f"device-trig worst abs deviation over the trajectory: {worst:.3e}")
 

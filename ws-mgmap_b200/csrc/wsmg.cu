@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
 }
 
 // ------------------------------------------------------------------ k_fused
-template <int CE, int CG, bool VEC>
+template <int CE, int CG, int CHW, bool VEC>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  fused_body<CE, CG, VEC>(p, blockIdx.x, smem, threadIdx.x, blockDim.x);
+  fused_body<FUSED_THREADS, CE, CG, CHW, VEC>(p, blockIdx.x, smem, threadIdx.x);
 }
 
 // ------------------------------------------------------------------ host glue
@@ -104,11 +104,11 @@ static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8
   return (int)cudaGetLastError();
 }
 
-template <int CE, int CG, bool VEC>
+template <int CE, int CG, int CHW, bool VEC>
 static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
   if (e != cudaSuccess) return (int)e;
-  k_fused<CE, CG, VEC><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
+  k_fused<CE, CG, CHW, VEC><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -124,9 +124,10 @@ static int launch_fused(FusedParams p, cudaStream_t s) {
   const bool vec = (p.g.C % 4) == 0;
   const int grid = p.bs * ((p.g.C + SLAB - 1) / SLAB);
   const char* force = getenv("WSMG_FORCE_GENERIC");
-  if (vec && p.g.E == 100 && p.g.G == 240 && !(force && force[0] == '1')) return launch_fused_t<100, 240, true>(p, grid, s);
-  if (vec) return launch_fused_t<0, 0, true>(p, grid, s);
-  return launch_fused_t<0, 0, false>(p, grid, s);
+  const bool ref_shape = vec && p.g.E == 100 && p.g.G == 240 && p.g.Hf * p.g.Wf == 224 * 224;
+  if (ref_shape && !(force && force[0] == '1')) return launch_fused_t<100, 240, 224 * 224, true>(p, grid, s);
+  if (vec) return launch_fused_t<0, 0, 0, true>(p, grid, s);
+  return launch_fused_t<0, 0, 0, false>(p, grid, s);
 }
 
 }  // namespace wsmg

@@ -1,24 +1,26 @@
 // Body of the fused map-update CTA, written once and compiled twice:
 //   * by nvcc as the device code of k_fused (wsmg.cu), one CTA per (env, 4-channel slab);
-//   * by g++ as a serial emulation (wsmg_emul.cpp, tid0 = 0 / stride = 1) that the CPU
-//     tests compare against the oracle.  The emulation is test infrastructure; nothing
-//     in the product path calls it.
+//   * by g++ as a serial emulation (wsmg_emul.cpp, NT = 1) that the CPU tests compare against
+//     the oracle.  The emulation is test infrastructure; nothing in the product path calls it.
 //
-// The kernel is instruction-issue bound before it is HBM bound (ncu, profiles/), so the
-// code below trades shared-memory tables for instructions everywhere:
-//   * every bilinear tap is `table lookup -> add -> max(.,0) -> LDS.128`; index 0 of X, of
-//     the fan and of the F ring is a zero cell that out-of-range taps resolve to;
-//   * the thread -> window-cell mapping of the fuse bands is fixed, so the loop carries only
-//     a pointer increment;
-//   * the reference geometry (E=100, G=240) is a template instantiation, divisions by E and
-//     E+2 become multiplies.
+// The kernel is instruction-issue bound before it is HBM bound (ncu, profiles/), so the code
+// trades shared-memory tables and compile-time constants for instructions everywhere:
+//   * CTA size, ego/global size and the feature-plane stride are template constants for the
+//     reference shapes; single-trip loops collapse to an `if`, divisions to multiplies, channel
+//     plane offsets to immediates;
+//   * every bilinear tap is `table entry + table entry -> max(.,0) -> LDS.128`; index 0 of X
+//     and of the fan / F ring is a zero cell that every out-of-range tap resolves to;
+//   * the scatter keeps per-value work branch-free (select, max, 2-op key, predicated ATOMS).
 //
-// Shared-memory plan (E=100, G=240: 230.7 KB of the 227 KiB an sm_100 CTA may opt in to):
-//   X    [1 + E*E] F4    zero cell + rotated ego grid R, later the back-translated crop B
-//   P    planar u32 keys [4][npp] during the scatter, then F4[1 + fan_cells] (zero cell first);
-//        after the first rotation the region is reused for the F ring + translate tables
-//   Gst  2 x [BAND*WW] F4   cp.async-staged bands of the caller's global map window
-//   tail baseE[E], fanrow[E+1], flags
+// Shared memory (E=100, G=240: 229.7 KB of the 227 KiB = 232448 B a CTA may opt in to):
+//   X     [1 + E*E] F4    zero cell + rotated ego grid R; rows are overwritten by the crop B
+//   Z     1 F4            zero cell shared by the fan and the F ring (sits right before R2)
+//   R2    scatter: planar u32 keys [4][npp], then F4[fan_cells];
+//         afterwards: F ring, `rr` window rows of WW cells.  The map window is cp.async'ed
+//         straight into its ring row and max-fused IN PLACE; band 0 lands beyond the key
+//         planes so that it can stream in underneath the scatter.
+//   T     colT[WW], rowT[WW], bXT[E], bYT[E] (I4 each): the two separable translations
+//   tail  baseE[E], fanrow[E+1], flags
 #pragma once
 #include "wsmg_math.h"
 
@@ -32,10 +34,9 @@
 
 namespace wsmg {
 
-constexpr int SLAB = 4;     // channels per CTA
-constexpr int BAND = 8;     // window rows per fuse band
-constexpr int RING = BAND + 2;
-constexpr int NEG = -(1 << 24);   // "tap out of range": any index sum containing it is negative
+constexpr int SLAB = 4;            // channels per CTA
+constexpr int BAND = 9;            // window rows per fuse band
+constexpr int NEG = -(1 << 24);    // "tap out of range": any index sum containing it is negative
 
 struct alignas(16) F4 { float v[4]; };
 struct alignas(16) I4 { int a, b, c, d; };
@@ -57,10 +58,21 @@ WSMG_HD int as_int(float f) {
 }
 WSMG_HD int imax0(int a) { return a > 0 ? a : 0; }
 
+constexpr int fan_cells_of(int E) {
+  int rows = E / 2 + 1 < E ? E / 2 + 1 : E, n = 0;
+  for (int y = 0; y < rows; ++y) {
+    int lo = y - 2 > 0 ? y - 2 : 0, hi = E - y + 1 < E - 1 ? E - y + 1 : E - 1;
+    n += hi - lo + 1 > 0 ? hi - lo + 1 : 0;
+  }
+  return n;
+}
+constexpr int npp_of(int fan_cells) { return (fan_cells + 3) & ~3; }
+
 struct SmemPlan {
-  int x_off, p_off, p_bytes, gst_off, base_off, fanrow_off, flag_off, total;
-  int npp;                 // words per key plane during the scatter
-  int ring_off, tab_off;   // views inside the P region after the first rotation
+  int x_off, z_off, r2_off, tab_off, base_off, fanrow_off, flag_off, total;
+  int npp;        // words per key plane during the scatter
+  int rr;         // ring rows
+  int s0;         // ring slot of window row 0 (first slot beyond the key planes)
 };
 
 WSMG_HD int align16(int x) { return (x + 15) & ~15; }
@@ -68,17 +80,14 @@ WSMG_HD int align16(int x) { return (x + 15) & ~15; }
 WSMG_HD SmemPlan make_plan(const Geo& g) {
   SmemPlan s;
   const int WW = g.E + 2;
-  s.npp = (g.fan_cells + 1 + 3) & ~3;
+  s.npp = npp_of(g.fan_cells);
+  s.s0 = (s.npp + WW - 1) / WW;
+  s.rr = 4 * BAND + 2 > s.s0 + BAND ? 4 * BAND + 2 : s.s0 + BAND;
   s.x_off = 0;
-  s.p_off = align16((1 + g.E * g.E) * 16);
-  int p_scatter = s.npp * 16;
-  int ring_bytes = (1 + RING * WW) * 16;
-  int tab_bytes = (2 * WW + 2 * g.E) * 16;
-  s.ring_off = s.p_off;
-  s.tab_off = s.p_off + ring_bytes;
-  s.p_bytes = p_scatter > ring_bytes + tab_bytes ? p_scatter : ring_bytes + tab_bytes;
-  s.gst_off = s.p_off + align16(s.p_bytes);
-  s.base_off = s.gst_off + 2 * BAND * WW * 16;
+  s.z_off = (1 + g.E * g.E) * 16;
+  s.r2_off = s.z_off + 16;
+  s.tab_off = s.r2_off + s.rr * WW * 16;
+  s.base_off = s.tab_off + (2 * WW + 2 * g.E) * 16;
   s.fanrow_off = s.base_off + align16(g.E * 4);
   s.flag_off = s.fanrow_off + align16((g.E + 1) * 8);
   s.total = s.flag_off + 16;
@@ -147,29 +156,41 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 }
 
 // ------------------------------------------------------------------ the CTA body
-// CE/CG > 0: geometry known at compile time (the reference's 100/240); 0: read it from p.g.
+// NT: threads per CTA (1 in the emulation).  CE/CG/CHW > 0: ego size, global size and Hf*Wf known
+// at compile time (the reference's 100 / 240 / 224*224); 0: read from p.g.
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
-template <int CE, int CG, bool VEC>
-WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, int tid0, int ts) {
+template <int NT, int CE, int CG, int CHW, bool VEC>
+WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, const int tid) {
   const Geo& g = p.g;
+  const SmemPlan& sp = p.sp;
   const int E = CE > 0 ? CE : g.E;
   const int G = CG > 0 ? CG : g.G;
+  const int HW = CHW > 0 ? CHW : g.Hf * g.Wf;
   const int C = g.C, WW = E + 2, EE = E * E;
-  const int HW = g.Hf * g.Wf;
+  const int fan_cells = CE > 0 ? fan_cells_of(CE) : g.fan_cells;
+  const int npp = CE > 0 ? npp_of(fan_cells_of(CE)) : sp.npp;
+  const int RR = CE > 0 ? (4 * BAND + 2 > (npp_of(fan_cells_of(CE)) + CE + 1) / (CE + 2) + BAND
+                               ? 4 * BAND + 2 : (npp_of(fan_cells_of(CE)) + CE + 1) / (CE + 2) + BAND)
+                        : sp.rr;
+  const int S0 = CE > 0 ? (npp_of(fan_cells_of(CE)) + CE + 1) / (CE + 2) : sp.s0;
   const int slabs = (C + SLAB - 1) / SLAB;
   const int b = block / slabs;
   const int c0 = (block - b * slabs) * SLAB;
   const int nch = (C - c0) < SLAB ? (C - c0) : SLAB;
-  const SmemPlan& sp = p.sp;
   const int paste_lo = G / 2 - E / 2;
   const float half_e = (float)E / 2.0f, half_g = (float)G / 2.0f, gcenter = (float)(G / 2);
+  const int NB = (WW + BAND - 1) / BAND;
 
-  F4* X = reinterpret_cast<F4*>(smem + sp.x_off);          // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
-  uint32_t* Pk = reinterpret_cast<uint32_t*>(smem + sp.p_off);
-  F4* Pf = reinterpret_cast<F4*>(smem + sp.p_off);         // Pf[0] = zero cell, fan cell c at Pf[1 + c]
-  F4* Gst = reinterpret_cast<F4*>(smem + sp.gst_off);
+  F4* X = reinterpret_cast<F4*>(smem + sp.x_off);            // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
+  uint32_t* Pk = reinterpret_cast<uint32_t*>(smem + sp.r2_off);
+  F4* Pf = reinterpret_cast<F4*>(smem + sp.z_off);           // Pf[0] = zero cell, fan cell c at Pf[1 + c]
+  F4* ring = reinterpret_cast<F4*>(smem + sp.z_off);         // ring[0] = zero cell, (slot, col) at ring[1 + slot*WW + col]
+  I4* colT = reinterpret_cast<I4*>(smem + sp.tab_off);
+  I4* rowT = colT + WW;
+  I4* bXT = rowT + WW;
+  I4* bYT = bXT + E;
   float* baseE = reinterpret_cast<float*>(smem + sp.base_off);
-  I2* fanrow = reinterpret_cast<I2*>(smem + sp.fanrow_off); // per grid row y (entry E = "no such row"): {1+rowoff-xs, xs | xe<<16}
+  I2* fanrow = reinterpret_cast<I2*>(smem + sp.fanrow_off);   // per grid row y (entry E = "no such row"): {1+rowoff-xs, xs | xe<<16}
   int* flags = reinterpret_cast<int*>(smem + sp.flag_off);
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63
@@ -189,31 +210,30 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     gmap_b = p.gmap + (size_t)b * G * G * C + c0;
   }
 
-  // cp.async one band of the caller's map window into Gst[k&1]; cells outside the map are zero-filled
+  // cp.async band k of the caller's map window into its ring rows; cells outside the map are zero-filled
   auto prefetch_band = [&](int k) {
-    F4* dst = Gst + (k & 1) * BAND * WW;
-    for (int t = tid0; t < BAND * WW; t += ts) {
+    for (int t = tid; t < BAND * WW; t += NT) {
       int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
-      int u = u0 + uu, v = v0 + vv;
-      bool inside = uu < WW && (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
-      const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
-      if (VEC) {
-        async_copy16(dst + t, src, inside);
-      } else {
-        for (int ch = 0; ch < SLAB; ++ch) async_copy4(&dst[t].v[ch], src + (ch < nch ? ch : 0), inside && ch < nch);
+      if (uu < WW) {
+        int u = u0 + uu, v = v0 + vv;
+        bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
+        const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
+        F4* dst = ring + 1 + ((uu + S0) % RR) * WW + vv;
+        if (VEC) {
+          async_copy16(dst, src, inside);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch) async_copy4(&dst->v[ch], src + (ch < nch ? ch : 0), inside && ch < nch);
+        }
       }
     }
     async_commit();
   };
-  const int NB = (WW + BAND - 1) / BAND;
-  if (!p.stop_after_scatter) {        // the map window streams in underneath the scatter
-    prefetch_band(0);
-    if (NB > 1) prefetch_band(1);
-  }
+  if (!p.stop_after_scatter) prefetch_band(0);     // streams in underneath the scatter (slots beyond the key planes)
 
   // ---- tables ------------------------------------------------------------------------------
-  for (int t = tid0; t < E; t += ts) baseE[t] = base_coord(t, E);
-  for (int t = tid0; t <= E; t += ts) {
+  for (int t = tid; t < E; t += NT) baseE[t] = base_coord(t, E);
+  for (int t = tid; t <= E; t += NT) {
     I2 fr; fr.a = 0; fr.b = 1;                              // xs = 1 > xe = 0: empty row
     if (t < g.fan_rows) {
       int off = 0;
@@ -223,8 +243,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
     fanrow[t] = fr;
   }
-  if (tid0 == 0) { flags[0] = 0; X[0] = f4_zero(); }
-  for (int t = tid0; t < SLAB * sp.npp; t += ts) Pk[t] = 0u;
+  if (tid == 0) { flags[0] = 0; X[0] = f4_zero(); Pf[0] = f4_zero(); }
+  for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = 0u;
   WSMG_SYNC();
 
   // ---- phase 1: scatter-max into the packed fan (rgb_mapping.py:210-225) -----------------------
@@ -233,14 +253,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const float* plane0 = p.feat + ((size_t)b * C + c0) * HW;
     const int n4 = HW / 4;
     int saw_invalid = 0;
-    for (int t = tid0; t < n4; t += 2 * ts) {
+    for (int t = tid; t < n4; t += 2 * NT) {
       // two 4-pixel groups per trip so that 8 feature loads are in flight per thread
       uint2 cc[2];
       bool live[2];
       F4 f[2][SLAB];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        int tt = t + h * ts;
+        const int tt = t + h * NT;
         cc[h].x = cc[h].y = 0xFFFFFFFFu;
         if (tt < n4) cc[h] = ld_codes(codes4 + tt);
       }
@@ -248,7 +268,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       bool ok[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        int tt = t + h * ts;
+        const int tt = t + h * NT;
         code[h][0] = cc[h].x & 0xFFFFu; code[h][1] = cc[h].x >> 16;
         code[h][2] = cc[h].y & 0xFFFFu; code[h][3] = cc[h].y >> 16;
 #pragma unroll
@@ -257,29 +277,32 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         const bool all_ok = ok[h][0] && ok[h][1] && ok[h][2] && ok[h][3];
         if (tt < n4 && !all_ok) saw_invalid = 1;
         live[h] = tt < n4 && any_ok;                 // a group where no pixel writes skips its feature read
+        const float* src = plane0 + 4 * (size_t)tt;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
-          if (live[h] && ch < nch) f[h][ch] = ld_stream4(plane0 + (size_t)ch * HW + 4 * (size_t)tt);
+          if (live[h] && ch < nch) f[h][ch] = ld_stream4(src + (size_t)ch * HW);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (!live[h]) continue;
-        bool last[4];
-        last[0] = code[h][1] != code[h][0]; last[1] = code[h][2] != code[h][1];
-        last[2] = code[h][3] != code[h][2]; last[3] = true;
+        // runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
+        // finish_cell() turns -0 into +0 like the reference): one shared-memory atomic per run.
+        // Per value: select, max, 2-op key, predicated ATOMS, select -- no branches.
+        bool flush[4], last[3];
+        last[0] = code[h][1] != code[h][0]; last[1] = code[h][2] != code[h][1]; last[2] = code[h][3] != code[h][2];
+        flush[0] = ok[h][0] && last[0]; flush[1] = ok[h][1] && last[1]; flush[2] = ok[h][2] && last[2]; flush[3] = ok[h][3];
+        uint32_t* cell[4];
+#pragma unroll
+        for (int px = 0; px < 4; ++px) cell[px] = Pk + (ok[h][px] ? code[h][px] : 0u);
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch) {
           if (ch >= nch) break;
-          uint32_t* plane = Pk + ch * sp.npp;
-          // runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
-          // finish_cell() turns -0 into +0 like the reference), one shared-memory atomic per run
           float run = -INFINITY;
 #pragma unroll
           for (int px = 0; px < 4; ++px) {
-            if (ok[h][px]) {
-              run = fmaxf(run, f[h][ch].v[px]);
-              if (last[px]) { smem_max(plane + code[h][px], f2key(run)); run = -INFINITY; }
-            }
+            run = fmaxf(run, ok[h][px] ? f[h][ch].v[px] : -INFINITY);
+            if (flush[px]) smem_max(cell[px] + ch * npp, f2key(run));
+            if (px < 3) run = last[px] ? -INFINITY : run;
           }
         }
       }
@@ -292,33 +315,31 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   if (p.proj_in == nullptr) {
     const uint32_t sentinel_key = f2key(SENTINEL);
     const bool inv = flags[0] != 0;
-    for (int t = tid0; t < g.fan_cells; t += ts) {
+    for (int t = tid; t < fan_cells; t += NT) {
       F4 v;
 #pragma unroll
       for (int ch = 0; ch < SLAB; ++ch) {
-        uint32_t k = Pk[ch * sp.npp + t];
+        uint32_t k = Pk[ch * npp + t];
         if (t == 0 && inv && k < sentinel_key) k = sentinel_key;   // invalid pixels write -1e16 to cell 0 (:207-212)
         v.v[ch] = ch < nch ? finish_cell(k) : 0.0f;
       }
       X[1 + t] = v;
     }
     WSMG_SYNC();
-    for (int t = tid0; t < g.fan_cells; t += ts) Pf[1 + t] = X[1 + t];
-    if (tid0 == 0) Pf[0] = f4_zero();
+    for (int t = tid; t < fan_cells; t += NT) Pf[1 + t] = X[1 + t];
   } else {
     // stage API: load the projection (zero outside the fan by construction)
     const float* src = p.proj_in + ((size_t)b * C + c0) * EE;
     for (int y = 0; y < g.fan_rows; ++y) {
       int xs = fan_x_lo(y), w = fan_row_width(y, E);
       int base = fanrow[y].a + xs;
-      for (int t = tid0; t < w; t += ts) {
+      for (int t = tid; t < w; t += NT) {
         F4 v;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch) v.v[ch] = ch < nch ? src[(size_t)ch * EE + y * E + xs + t] : 0.0f;
         Pf[base + t] = v;
       }
     }
-    if (tid0 == 0) Pf[0] = f4_zero();
   }
   WSMG_SYNC();
 
@@ -330,7 +351,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 
   if (p.proj_out != nullptr) {
     float* dst = p.proj_out + ((size_t)b * C + c0) * EE;
-    for (int t = tid0; t < EE; t += ts) {
+    for (int t = tid; t < EE; t += NT) {
       int y = t / E, x = t - y * E;
       F4 v = Pf[fan_idx(fanrow[y], x)];
 #pragma unroll
@@ -344,7 +365,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float cs, sn;
   if (p.trig != nullptr) { cs = p.trig[4 * b + 0]; sn = p.trig[4 * b + 1]; }
   else { float h = -p.compass[b]; sn = sinf(h); cs = cosf(h); }
-  for (int t = tid0; t < EE; t += ts) {
+  for (int t = tid; t < EE; t += NT) {
     int i = t / E, j = t - i * E;
     float ix, iy;
     rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
@@ -357,17 +378,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     F4 c = Pf[fan_idx(r1, tx.i0)], d = Pf[fan_idx(r1, tx.i0 + 1)];
     X[1 + t] = blend_f4(a, bb, c, d, w);
   }
-  WSMG_SYNC();
 
   // ---- phase 3 tables: the two (separable) translations (rgb_mapping.py:45-53, 57-65) ----------
-  // colT[vv] = {x0 or NEG, x0+1 or NEG, bits(wx), inside};   rowT[uu] = {1 + y0*E or NEG, 1 + (y0+1)*E or NEG, bits(wy), inside}
-  // bXT[q]   = {col0 or NEG, col1 or NEG, bits(wx), 0};      bYT[p]   = {1 + slot(row0)*WW or NEG, 1 + slot(row1)*WW or NEG, bits(wy), 0}
-  I4* colT = reinterpret_cast<I4*>(smem + sp.tab_off);
-  I4* rowT = colT + WW;
-  I4* bXT = rowT + WW;
-  I4* bYT = bXT + E;
-  F4* ring = reinterpret_cast<F4*>(smem + sp.ring_off);     // ring[0] = zero cell
-  for (int t = tid0; t < WW; t += ts) {
+  // colT[vv] = {x0 | NEG, x0+1 | NEG, bits(wx), column inside the map}
+  // rowT[uu] = {1 + y0*E | NEG, 1 + (y0+1)*E | NEG, bits(wy), 1 + slot(uu)*WW if the row is inside the map else NEG}
+  // bXT[q]   = {col0 | NEG, col1 | NEG, bits(wx), 0}
+  // bYT[p]   = {1 + slot(row0)*WW | NEG, 1 + slot(row1)*WW | NEG, bits(wy), 0}       (slot(r) = (r + S0) % RR)
+  for (int t = tid; t < WW; t += NT) {
     int v = v0 + t, u = u0 + t;
     I4 ct; ct.a = ct.b = NEG; ct.c = 0; ct.d = 0;
     if ((unsigned)v < (unsigned)G) {    // canvas column sampled by global column v, relative to the pasted ego grid
@@ -378,17 +395,17 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       ct.c = as_int(tp.w1); ct.d = 1;
     }
     colT[t] = ct;
-    I4 rt; rt.a = rt.b = NEG; rt.c = 0; rt.d = 0;
+    I4 rt; rt.a = rt.b = NEG; rt.c = 0; rt.d = NEG;
     if ((unsigned)u < (unsigned)G) {
       Tap1D tp = make_tap(unnormalize(base_coord(u, G) + (-qy), half_g));
       int y0 = tp.i0 - paste_lo;
       rt.a = (unsigned)y0 < (unsigned)E ? 1 + y0 * E : NEG;
       rt.b = (unsigned)(y0 + 1) < (unsigned)E ? 1 + (y0 + 1) * E : NEG;
-      rt.c = as_int(tp.w1); rt.d = 1;
+      rt.c = as_int(tp.w1); rt.d = 1 + ((t + S0) % RR) * WW;
     }
     rowT[t] = rt;
   }
-  for (int t = tid0; t < E; t += ts) {   // global column / row sampled by crop cell t, relative to the window
+  for (int t = tid; t < E; t += NT) {   // global column / row sampled by crop cell t, relative to the window
     Tap1D tp = make_tap(unnormalize(base_coord(t + paste_lo, G) + qx, half_g));
     int cx = tp.i0 - v0;
     I4 bx; bx.a = (unsigned)cx < (unsigned)WW ? cx : NEG; bx.b = (unsigned)(cx + 1) < (unsigned)WW ? cx + 1 : NEG;
@@ -396,57 +413,63 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     bXT[t] = bx;
     Tap1D tq = make_tap(unnormalize(base_coord(t + paste_lo, G) + qy, half_g));
     int ry = tq.i0 - u0;
-    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + (ry % RING) * WW : NEG;
-    by.b = (unsigned)(ry + 1) < (unsigned)WW ? 1 + ((ry + 1) % RING) * WW : NEG;
+    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + ((ry + S0) % RR) * WW : NEG;
+    by.b = (unsigned)(ry + 1) < (unsigned)WW ? 1 + ((ry + 1 + S0) % RR) * WW : NEG;
     by.c = as_int(tq.w1); by.d = 0;
     bYT[t] = by;
   }
-  if (tid0 == 0) ring[0] = f4_zero();
-  WSMG_SYNC();
+  WSMG_SYNC();                     // R complete, fan dead: the key planes may now be overwritten by ring rows
+  if (NB > 1) prefetch_band(1);
 
   // ---- phase 3: banded translate + max-fuse (:53-56) and translate back + crop (:64-69) -------
-  // BAND*WW and RING*E are below the CTA size: each loop below is one trip per thread and band.
+  // Trip k fuses band k (F rows [kB, kB+B)) in place in the ring and, independently, back-translates
+  // the crop rows whose F rows were finished by trip k-1: B row p reads F rows p..p+2 and overwrites
+  // X row p, which only F rows p..p+2 read -- so rows p <= done-3 are safe.  One barrier per trip.
   int p_lo = 0;
-  for (int k = 0; k < NB; ++k) {
-    if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
-    WSMG_SYNC();
-    const F4* gst = Gst + (k & 1) * BAND * WW;
-    for (int t = tid0; t < BAND * WW; t += ts) {
-      int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
-      if (uu >= WW) continue;
-      const I4 ct = colT[vv], rt = rowT[uu];
-      F4 f = f4_zero();
-      if (ct.d & rt.d) {
-        Weights w = make_weights(as_float(ct.c), as_float(rt.c));
-        F4 a = X[imax0(rt.a + ct.a)], bb = X[imax0(rt.a + ct.b)], c = X[imax0(rt.b + ct.a)], d = X[imax0(rt.b + ct.b)];
-        F4 tv = blend_f4(a, bb, c, d, w);
-        F4 old = gst[t];
-#pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(old.v[ch], tv.v[ch]);
-        float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
-        if (VEC) {
-          *reinterpret_cast<F4*>(dst) = f;
-        } else {
-#pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch)
-            if (ch < nch) dst[ch] = f.v[ch];
-        }
-      }
-      ring[1 + (uu % RING) * WW + vv] = f;
+  for (int k = 0; k <= NB; ++k) {
+    if (k < NB) {
+      if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
     }
     WSMG_SYNC();
     if (k + 2 < NB) prefetch_band(k + 2);
-    // B rows whose three source rows of F (and hence all readers of R row p) are done
-    int done = (k + 1) * BAND < WW ? (k + 1) * BAND : WW;
-    int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
-    for (int t = tid0; t < (p_hi - p_lo) * E; t += ts) {
-      int dr = t / E, q = t - dr * E, pr = p_lo + dr;
-      const I4 bx = bXT[q], by = bYT[pr];
-      Weights w = make_weights(as_float(bx.c), as_float(by.c));
-      F4 a = ring[imax0(by.a + bx.a)], bb = ring[imax0(by.a + bx.b)], c = ring[imax0(by.b + bx.a)], d = ring[imax0(by.b + bx.b)];
-      X[1 + pr * E + q] = blend_f4(a, bb, c, d, w);
+    else async_commit();                                    // keep one group per trip so wait<1> stays exact
+    if (k < NB) {
+      for (int t = tid; t < BAND * WW; t += NT) {
+        int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
+        if (uu >= WW) continue;
+        const I4 ct = colT[vv], rt = rowT[uu];
+        if (ct.d > 0 && rt.d > 0) {
+          Weights w = make_weights(as_float(ct.c), as_float(rt.c));
+          F4 a = X[imax0(rt.a + ct.a)], bb = X[imax0(rt.a + ct.b)], c = X[imax0(rt.b + ct.a)], d = X[imax0(rt.b + ct.b)];
+          F4 tv = blend_f4(a, bb, c, d, w);
+          F4* cellp = ring + rt.d + vv;
+          F4 f = *cellp;
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(f.v[ch], tv.v[ch]);
+          *cellp = f;
+          float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
+          if (VEC) {
+            *reinterpret_cast<F4*>(dst) = f;
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < SLAB; ++ch)
+              if (ch < nch) dst[ch] = f.v[ch];
+          }
+        }
+      }
     }
-    p_lo = p_hi;
+    if (k >= 1) {
+      int done = k * BAND < WW ? k * BAND : WW;            // F rows finished before this trip
+      int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
+      for (int t = tid; t < (p_hi - p_lo) * E; t += NT) {
+        int dr = t / E, q = t - dr * E, pr = p_lo + dr;
+        const I4 bx = bXT[q], by = bYT[pr];
+        Weights w = make_weights(as_float(bx.c), as_float(by.c));
+        F4 a = ring[imax0(by.a + bx.a)], bb = ring[imax0(by.a + bx.b)], c = ring[imax0(by.b + bx.a)], d = ring[imax0(by.b + bx.b)];
+        X[1 + pr * E + q] = blend_f4(a, bb, c, d, w);
+      }
+      p_lo = p_hi;
+    }
   }
   WSMG_SYNC();
 
@@ -454,7 +477,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   if (p.trig != nullptr) { cs = p.trig[4 * b + 2]; sn = p.trig[4 * b + 3]; }
   else { float h = p.compass[b]; sn = sinf(h); cs = cosf(h); }
   float* ego_b = p.ego + ((size_t)b * C + c0) * EE;
-  for (int t = tid0; t < EE; t += ts) {
+  for (int t = tid; t < EE; t += NT) {
     int i = t / E, j = t - i * E;
     float ix, iy;
     rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);

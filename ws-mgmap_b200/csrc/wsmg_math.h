@@ -53,7 +53,7 @@ WSMG_HD uint32_t f2key(float f) {
 #else
   uint32_t b; __builtin_memcpy(&b, &f, 4);
 #endif
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // negative: ~b, else b | sign
 }
 WSMG_HD float key2f(uint32_t k) {
   uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
