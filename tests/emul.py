@@ -9,7 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-_pkg = importlib.import_module("ws-mgmap_b200")
+import wsmgmap_b200  # noqa: E402,F401
 from wsmgmap_b200._lib import WsmgDims, make_dims  # noqa: E402
 from wsmgmap_b200.build import build_emulation  # noqa: E402
 
@@ -35,7 +35,7 @@ def emul_cells(depth, hf, e=100, g=240, res=0.12):
     lin = np.zeros((bs, hf, hf), np.int32)
     inv = np.zeros((bs, hf, hf), np.uint8)
     codes = np.zeros((bs, hf, hf), np.uint16)
-    rc = lib().wsmg_emul_unproject_index(_p(np.ascontiguousarray(depth)), _p(lin), _p(inv), _p(codes), ctypes.byref(d))
+    rc = lib().wsmg_emul_unproject_index(_p(np.ascontiguousarray(depth)), _p(lin), _p(inv), _p(codes), None, ctypes.byref(d))
     assert rc == 0, rc
     return lin, inv.astype(bool), codes
 

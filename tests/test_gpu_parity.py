@@ -222,3 +222,37 @@ def test_error_codes():
     with pytest.raises(_lib.WsmgError, match="shared memory"):
         ops.map_update(feat, depth, torch.zeros(1, 2, device=DEV), torch.zeros(1, 1, device=DEV),
                        torch.zeros(1, 1, device=DEV), torch.zeros(1, 480, 480, 64, device=DEV), e=200)
+
+
+def test_kernel_variants_agree():
+    """The four builds of the fused kernel (TMA vs cp.async window path, compile-time vs run-time
+    geometry) are bit-identical over a short trajectory that includes a border-clipped window."""
+    import os
+    bs, c, hf, hd = 6, 64, 224, 256
+    gen = torch.Generator().manual_seed(21)
+    frames = []
+    walk = RandomWalk(bs, seed=5, far_env=0)
+    for t in range(4):
+        gps, compass, masks = walk.step()
+        if t >= 2:
+            gps[0] += torch.tensor([10.0, -9.0])
+        frames.append((make_features(bs, c, hf, hf, gen).to(DEV), make_depth(("room2", "uniform", "near", "room4")[t], bs, hd, hd, gen).to(DEV),
+                       gps.to(DEV), compass.to(DEV), masks.to(DEV)))
+    results = {}
+    try:
+        for no_tma in ("0", "1"):
+            for generic in ("0", "1"):
+                os.environ["WSMG_NO_TMA"] = no_tma
+                os.environ["WSMG_FORCE_GENERIC"] = generic
+                gmap = torch.zeros(bs, 240, 240, c, device=DEV)
+                egos = [ops.map_update(f, d, g, cp, m, gmap).clone() for f, d, g, cp, m in frames]
+                torch.cuda.synchronize()
+                results[(no_tma, generic)] = (egos, gmap)
+    finally:
+        os.environ.pop("WSMG_NO_TMA", None)
+        os.environ.pop("WSMG_FORCE_GENERIC", None)
+    ref_egos, ref_map = results[("0", "0")]
+    for key, (egos, gmap) in results.items():
+        assert torch.equal(gmap, ref_map), key
+        for a, b in zip(egos, ref_egos):
+            assert torch.equal(a, b), key

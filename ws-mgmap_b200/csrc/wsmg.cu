@@ -7,8 +7,10 @@
 //             max-fuse into the map window, translate back, crop, rotate -> NCHW ego map
 //             (rgb_mapping.py:210-232, 37-70).  Body in wsmg_body.h.
 // No tensor cores: the path is gather / scatter-max / bilinear streaming (~0.3 flop/byte).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "wsmg_body.h"
 #include "wsmg_host.h"
@@ -21,8 +23,10 @@ constexpr int CELLS_THREADS = 256;
 // ------------------------------------------------------------------ k_reset
 // full_global_map[:bs] *= masks (rgb_mapping.py:35).  mask == 1 (the steady state) touches nothing.
 __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
-                                               size_t per_env) {
+                                               size_t per_env, uint32_t* __restrict__ env_flags) {
   const int b = blockIdx.y;
+  if (env_flags != nullptr && blockIdx.x == 0 && threadIdx.x == 0) env_flags[b] = 0u;   // k_cells (next launch) sets them
+  if (gmap == nullptr) return;
   const float m = mask[b];
   if (m == 1.0f) return;
   float* base = gmap + (size_t)b * per_env;
@@ -51,7 +55,7 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
 // kernel scatters with and/or the reference-shaped (linear index, invalid) pair of the stage API.
 __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
                                                           int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
-                                                          Geo g) {
+                                                          uint32_t* __restrict__ env_flags, Geo g) {
   __shared__ int rowoff[160];
   for (int t = threadIdx.x; t < g.fan_rows; t += blockDim.x) {
     int off = 0;
@@ -62,10 +66,17 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   const int b = blockIdx.y;
   const int HW = g.Hf * g.Wf;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= HW) return;
-  const int i = t / g.Wf, j = t - i * g.Wf;
-  int x, y;
-  const bool ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
+  const bool in_range = t < HW;
+  int x = 0, y = 0;
+  bool ok = true;
+  if (in_range) {
+    const int i = t / g.Wf, j = t - i * g.Wf;
+    ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
+  }
+  // invalid pixels write the sentinel to cell 0 (rgb_mapping.py:207-212): the fused kernel needs to know whether any exists
+  const unsigned any_bad = __ballot_sync(0xFFFFFFFFu, !ok);
+  if (env_flags != nullptr && any_bad != 0u && (threadIdx.x & 31) == 0) atomicOr(env_flags + b, 1u);
+  if (!in_range) return;
   if (codes != nullptr) {
     uint16_t code = CODE_INVALID;
     if (ok) {
@@ -79,41 +90,70 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
 }
 
 // ------------------------------------------------------------------ k_fused
-template <int CE, int CG, int CHW, bool VEC>
+template <int CE, int CG, int CHW, bool VEC, bool TMA>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  fused_body<FUSED_THREADS, CE, CG, CHW, VEC>(p, blockIdx.x, smem, threadIdx.x);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  fused_body<FUSED_THREADS, CE, CG, CHW, VEC, TMA>(p, blockIdx.x, smem, threadIdx.x);
 }
 
 // ------------------------------------------------------------------ host glue
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int launch_reset(float* gmap, const float* mask, const wsmg_dims* d, cudaStream_t s) {
+static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const wsmg_dims* d, cudaStream_t s) {
   const size_t per_env = (size_t)d->G * d->G * d->C;
-  dim3 grid(148 * 2, d->bs);
-  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env);
+  dim3 grid(gmap ? 148 * 2 : 1, d->bs);
+  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags);
   return (int)cudaGetLastError();
 }
 
-static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, const Geo& g, int bs,
-                        cudaStream_t s) {
+static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, uint32_t* env_flags,
+                        const Geo& g, int bs, cudaStream_t s) {
   if (g.fan_rows > 160) return WSMG_E_DIMS;
   const int HW = g.Hf * g.Wf;
   dim3 grid((HW + CELLS_THREADS - 1) / CELLS_THREADS, bs);
-  k_cells<<<grid, CELLS_THREADS, 0, s>>>(depth, codes, lin, invalid, g);
+  k_cells<<<grid, CELLS_THREADS, 0, s>>>(depth, codes, lin, invalid, env_flags, g);
   return (int)cudaGetLastError();
 }
 
-template <int CE, int CG, int CHW, bool VEC>
+// CUtensorMap of the caller's NHWC map [n_maps, G, G, C] with a one-window-row box {4 ch, E+2 cols, 1, 1}.
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
+static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const Geo& g) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;      // process-wide constant once resolved
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return (int)e;
+    if (ptr == nullptr || qres != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
+    fn = (encode_fn)ptr;
+  }
+  static_assert(sizeof(CUtensorMap) <= sizeof(TensorMapBlob), "tensor map blob too small");
+  CUtensorMap tm;
+  const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.G, (cuuint64_t)g.G, (cuuint64_t)n_maps};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.G * g.C * 4, (cuuint64_t)g.G * g.G * g.C * 4};
+  const cuuint32_t box[4] = {4, (cuuint32_t)(g.E + 2), 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gmap, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  memcpy(out->bytes, &tm, sizeof(tm));
+  return 0;
+}
+
+template <int CE, int CG, int CHW, bool VEC, bool TMA>
 static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
   if (e != cudaSuccess) return (int)e;
-  k_fused<CE, CG, CHW, VEC><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
+  k_fused<CE, CG, CHW, VEC, TMA><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
   return (int)cudaGetLastError();
 }
 
-// WSMG_FORCE_GENERIC=1 routes the reference geometry through the runtime-geometry kernel (tests).
-static int launch_fused(FusedParams p, cudaStream_t s) {
+// WSMG_FORCE_GENERIC=1 routes the reference shapes through the runtime-geometry kernel, WSMG_NO_TMA=1
+// moves the map window with cp.async / st.global instead of TMA (both for tests and A/B profiling).
+static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
   p.sp = make_plan(p.g);
   int dev = 0, max_optin = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -124,10 +164,21 @@ static int launch_fused(FusedParams p, cudaStream_t s) {
   const bool vec = (p.g.C % 4) == 0;
   const int grid = p.bs * ((p.g.C + SLAB - 1) / SLAB);
   const char* force = getenv("WSMG_FORCE_GENERIC");
+  const char* no_tma = getenv("WSMG_NO_TMA");
+  const bool generic = force && force[0] == '1';
+  bool tma = vec && !p.stop_after_scatter && !(no_tma && no_tma[0] == '1');
+  if (tma) {
+    int rc = encode_window_map(&p.tmap, p.gmap, n_maps, p.g);
+    if (rc != 0) return rc;
+  }
+  p.use_tma = tma ? 1 : 0;
   const bool ref_shape = vec && p.g.E == 100 && p.g.G == 240 && p.g.Hf * p.g.Wf == 224 * 224;
-  if (ref_shape && !(force && force[0] == '1')) return launch_fused_t<100, 240, 224 * 224, true>(p, grid, s);
-  if (vec) return launch_fused_t<0, 0, 0, true>(p, grid, s);
-  return launch_fused_t<0, 0, 0, false>(p, grid, s);
+  if (ref_shape && !generic) {
+    return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s)
+               : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s);
+  }
+  if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s) : launch_fused_t<0, 0, 0, true, false>(p, grid, s);
+  return launch_fused_t<0, 0, 0, false, false>(p, grid, s);
 }
 
 }  // namespace wsmg
@@ -165,17 +216,18 @@ static int map_update_impl(const float* feat, const float* depth, const float* g
   if (!aligned16(feat) || !aligned16(gmap) || !aligned16(scratch)) return WSMG_E_ALIGN;
   if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
   const Geo g = make_geo(d);
-  rc = launch_reset(gmap, mask, d, s);
-  if (rc) return rc;
   uint16_t* codes = (uint16_t*)scratch;
-  rc = launch_cells(depth, codes, nullptr, nullptr, g, d->bs, s);
+  uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
+  rc = launch_reset(gmap, mask, flags, d, s);
+  if (rc) return rc;
+  rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
-  p.feat = feat; p.codes = codes; p.gps = gps; p.compass = compass; p.trig = trig;
+  p.feat = feat; p.codes = codes; p.env_flags = flags; p.gps = gps; p.compass = compass; p.trig = trig;
   p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
   p.stop_after_scatter = 0; p.bs = d->bs; p.g = g;
   if (ev0) cudaEventRecord(ev0, s);
-  rc = launch_fused(p, s);
+  rc = launch_fused(p, d->n_maps, s);
   if (ev1) cudaEventRecord(ev1, s);
   return rc;
 }
@@ -199,7 +251,7 @@ int wsmg_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid, con
   int rc = validate_dims(d);
   if (rc != WSMG_OK) return rc;
   if (!depth || !lin || !invalid) return WSMG_E_NULL;
-  return launch_cells(depth, nullptr, lin, invalid, make_geo(d), d->bs, (cudaStream_t)stream);
+  return launch_cells(depth, nullptr, lin, invalid, nullptr, make_geo(d), d->bs, (cudaStream_t)stream);
 }
 
 int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out, void* scratch, size_t scratch_bytes_,
@@ -212,11 +264,14 @@ int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out, voi
   cudaStream_t s = (cudaStream_t)stream;
   const Geo g = make_geo(d);
   uint16_t* codes = (uint16_t*)scratch;
-  rc = launch_cells(depth, codes, nullptr, nullptr, g, d->bs, s);
+  uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
+  rc = launch_reset(nullptr, nullptr, flags, d, s);      // only clears the env flags
+  if (rc) return rc;
+  rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
-  p.feat = feat; p.codes = codes; p.proj_out = proj_out; p.stop_after_scatter = 1; p.bs = d->bs; p.g = g;
-  return launch_fused(p, s);
+  p.feat = feat; p.codes = codes; p.env_flags = flags; p.proj_out = proj_out; p.stop_after_scatter = 1; p.bs = d->bs; p.g = g;
+  return launch_fused(p, d->n_maps, s);
 }
 
 int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const float* compass, const float* mask,
@@ -226,12 +281,12 @@ int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const fl
   if (!proj_in || !gps || !compass || !mask || !gmap || !ego_out) return WSMG_E_NULL;
   if (!aligned16(gmap)) return WSMG_E_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  rc = launch_reset(gmap, mask, d, s);
+  rc = launch_reset(gmap, mask, nullptr, d, s);
   if (rc) return rc;
   FusedParams p{};
   p.proj_in = proj_in; p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap; p.ego = ego_out;
   p.bs = d->bs; p.g = make_geo(d);
-  return launch_fused(p, s);
+  return launch_fused(p, d->n_maps, s);
 }
 
 // ------------------------------------------------------------------ host-buffer entry

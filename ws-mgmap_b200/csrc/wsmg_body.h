@@ -16,9 +16,12 @@
 //   X     [1 + E*E] F4    zero cell + rotated ego grid R; rows are overwritten by the crop B
 //   Z     1 F4            zero cell shared by the fan and the F ring (sits right before R2)
 //   R2    scatter: planar u32 keys [4][npp], then F4[fan_cells];
-//         afterwards: F ring, `rr` window rows of WW cells.  The map window is cp.async'ed
-//         straight into its ring row and max-fused IN PLACE; band 0 lands beyond the key
-//         planes so that it can stream in underneath the scatter.
+//         afterwards: F ring, `rr` window rows of WWP cells (128-byte aligned rows).  Each row of
+//         the caller's map window is a TMA box {4 ch, WW cols, 1 row} copied straight into its
+//         ring row (mbarrier complete_tx; out-of-map cells arrive as zeros), max-fused IN PLACE
+//         and TMA-stored back (out-of-map cells are clipped): the 16-byte-per-cell NHWC gather
+//         never touches the LSU.  Band 0 lands beyond the key planes so that it streams in
+//         underneath the scatter.  (C % 4 != 0: cp.async / st.global fallback.)
 //   T     colT[WW], rowT[WW], bXT[E], bYT[E] (I4 each): the two separable translations
 //   tail  baseE[E], fanrow[E+1], flags
 #pragma once
@@ -69,32 +72,48 @@ constexpr int fan_cells_of(int E) {
 constexpr int npp_of(int fan_cells) { return (fan_cells + 3) & ~3; }
 
 struct SmemPlan {
-  int x_off, z_off, r2_off, tab_off, base_off, fanrow_off, flag_off, total;
+  int x_off, z_off, r2_off, tab_off, base_off, fanrow_off, bar_off, total;
   int npp;        // words per key plane during the scatter
   int rr;         // ring rows
   int s0;         // ring slot of window row 0 (first slot beyond the key planes)
+  int wwp;        // ring row stride in cells (row bytes are a multiple of 128 for TMA)
 };
+constexpr int MAX_BANDS = 32;
 
 WSMG_HD int align16(int x) { return (x + 15) & ~15; }
+
+constexpr int wwp_of(int E) { return (E + 2 + 7) & ~7; }
+constexpr int s0_of(int E) { return (npp_of(fan_cells_of(E)) + wwp_of(E) - 1) / wwp_of(E); }
+constexpr int rr_of(int E) { return 4 * BAND + 2 > s0_of(E) + BAND ? 4 * BAND + 2 : s0_of(E) + BAND; }
 
 WSMG_HD SmemPlan make_plan(const Geo& g) {
   SmemPlan s;
   const int WW = g.E + 2;
+  s.wwp = (WW + 7) & ~7;
   s.npp = npp_of(g.fan_cells);
-  s.s0 = (s.npp + WW - 1) / WW;
+  s.s0 = (s.npp + s.wwp - 1) / s.wwp;
   s.rr = 4 * BAND + 2 > s.s0 + BAND ? 4 * BAND + 2 : s.s0 + BAND;
   s.x_off = 0;
-  s.z_off = (1 + g.E * g.E) * 16;
-  s.r2_off = s.z_off + 16;
-  s.tab_off = s.r2_off + s.rr * WW * 16;
+  s.r2_off = ((1 + g.E * g.E) * 16 + 16 + 127) & ~127;      // 128-byte aligned: TMA destination rows
+  s.z_off = s.r2_off - 16;
+  s.tab_off = s.r2_off + s.rr * s.wwp * 16;
   s.base_off = s.tab_off + (2 * WW + 2 * g.E) * 16;
   s.fanrow_off = s.base_off + align16(g.E * 4);
-  s.flag_off = s.fanrow_off + align16((g.E + 1) * 8);
-  s.total = s.flag_off + 16;
+  s.bar_off = s.fanrow_off + align16((g.E + 1) * 8);
+  s.total = s.bar_off + MAX_BANDS * 8;
   return s;
 }
 
+#if defined(__CUDACC__)
+struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };   // a CUtensorMap, filled by the host glue
+#else
+struct TensorMapBlob { unsigned char bytes[8]; };
+#endif
+
 struct FusedParams {
+  TensorMapBlob tmap;       // [n_maps,G,G,C] fp32, box {4, E+2, 1, 1}; valid when use_tma
+  int use_tma;
+  const uint32_t* env_flags; // [bs] bit0: the env has at least one pixel that does not write (k_cells)
   const float* feat;        // [bs,C,Hf,Wf]
   const uint16_t* codes;    // [bs,Hf*Wf] packed fan codes from k_cells
   const float* gps;         // [bs,2]
@@ -133,6 +152,46 @@ __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_g
 template <int N> __device__ __forceinline__ void async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ unsigned saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// -- mbarrier / TMA (cp.async.bulk.tensor) -------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(saddr(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_row(void* dst, const void* tmap, int c, int v, int u, int b, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+               ::"r"(saddr(dst)), "l"(tmap), "r"(c), "r"(v), "r"(u), "r"(b), "r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_row(const void* tmap, int c, int v, int u, int b, const void* src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n"
+               ::"l"(tmap), "r"(c), "r"(v), "r"(u), "r"(b), "r"(saddr(src)) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// four predicated shared-memory max-reductions (one per channel plane), predicate evaluated in PTX:
+// the pixel writes (code < 0xFFFE) and closes its run (code != next).  No branch, no predicate spill.
+__device__ __forceinline__ void red_max4(uint32_t* cell, int npp, unsigned code, unsigned next,
+                                         uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+  unsigned a = saddr(cell);
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %4, %5;\n setp.lt.and.u32 p, %4, 0xFFFE, p;\n"
+               " @p red.shared.max.u32 [%0], %6;\n @p red.shared.max.u32 [%1], %7;\n"
+               " @p red.shared.max.u32 [%2], %8;\n @p red.shared.max.u32 [%3], %9;\n}\n"
+               ::"r"(a), "r"(a + 4 * npp), "r"(a + 8 * npp), "r"(a + 12 * npp), "r"(code), "r"(next),
+                 "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
+}
 #else
 inline void smem_max(uint32_t* a, uint32_t v) { if (v > *a) *a = v; }
 inline F4 ld_stream4(const float* p) { F4 r; for (int i = 0; i < 4; ++i) r.v[i] = p[i]; return r; }
@@ -146,6 +205,20 @@ inline void async_copy4(void* dst, const void* src, bool pred) {
 }
 inline void async_commit() {}
 template <int N> inline void async_wait() {}
+inline void mbar_init(uint64_t*, int) {}
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(uint64_t*, unsigned) {}
+inline void mbar_wait(uint64_t*, unsigned) {}
+inline void tma_load_row(void*, const void*, int, int, int, int, uint64_t*) {}
+inline void tma_store_row(const void*, int, int, int, int, const void*) {}
+inline void tma_commit() {}
+template <int N> inline void tma_wait_read() {}
+inline void fence_proxy_async() {}
+inline void red_max4(uint32_t* cell, int npp, unsigned code, unsigned next, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+  if (code < 0xFFFEu && code != next) {
+    smem_max(cell, k0); smem_max(cell + npp, k1); smem_max(cell + 2 * npp, k2); smem_max(cell + 3 * npp, k3);
+  }
+}
 #endif
 
 WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const Weights& w) {
@@ -159,7 +232,8 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 // NT: threads per CTA (1 in the emulation).  CE/CG/CHW > 0: ego size, global size and Hf*Wf known
 // at compile time (the reference's 100 / 240 / 224*224); 0: read from p.g.
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
-template <int NT, int CE, int CG, int CHW, bool VEC>
+// TMA: the map window moves through cp.async.bulk.tensor (needs VEC); else cp.async + st.global.
+template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA>
 WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, const int tid) {
   const Geo& g = p.g;
   const SmemPlan& sp = p.sp;
@@ -169,14 +243,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   const int C = g.C, WW = E + 2, EE = E * E;
   const int fan_cells = CE > 0 ? fan_cells_of(CE) : g.fan_cells;
   const int npp = CE > 0 ? npp_of(fan_cells_of(CE)) : sp.npp;
-  const int RR = CE > 0 ? (4 * BAND + 2 > (npp_of(fan_cells_of(CE)) + CE + 1) / (CE + 2) + BAND
-                               ? 4 * BAND + 2 : (npp_of(fan_cells_of(CE)) + CE + 1) / (CE + 2) + BAND)
-                        : sp.rr;
-  const int S0 = CE > 0 ? (npp_of(fan_cells_of(CE)) + CE + 1) / (CE + 2) : sp.s0;
+  const int WWP = CE > 0 ? wwp_of(CE) : sp.wwp;
+  const int RR = CE > 0 ? rr_of(CE) : sp.rr;
+  const int S0 = CE > 0 ? s0_of(CE) : sp.s0;
   const int slabs = (C + SLAB - 1) / SLAB;
   const int b = block / slabs;
   const int c0 = (block - b * slabs) * SLAB;
-  const int nch = (C - c0) < SLAB ? (C - c0) : SLAB;
+  const int nch = VEC ? SLAB : ((C - c0) < SLAB ? (C - c0) : SLAB);
   const int paste_lo = G / 2 - E / 2;
   const float half_e = (float)E / 2.0f, half_g = (float)G / 2.0f, gcenter = (float)(G / 2);
   const int NB = (WW + BAND - 1) / BAND;
@@ -184,14 +257,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   F4* X = reinterpret_cast<F4*>(smem + sp.x_off);            // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
   uint32_t* Pk = reinterpret_cast<uint32_t*>(smem + sp.r2_off);
   F4* Pf = reinterpret_cast<F4*>(smem + sp.z_off);           // Pf[0] = zero cell, fan cell c at Pf[1 + c]
-  F4* ring = reinterpret_cast<F4*>(smem + sp.z_off);         // ring[0] = zero cell, (slot, col) at ring[1 + slot*WW + col]
+  F4* ring = reinterpret_cast<F4*>(smem + sp.z_off);         // ring[0] = zero cell, (slot, col) at ring[1 + slot*WWP + col]
   I4* colT = reinterpret_cast<I4*>(smem + sp.tab_off);
   I4* rowT = colT + WW;
   I4* bXT = rowT + WW;
   I4* bYT = bXT + E;
   float* baseE = reinterpret_cast<float*>(smem + sp.base_off);
   I2* fanrow = reinterpret_cast<I2*>(smem + sp.fanrow_off);   // per grid row y (entry E = "no such row"): {1+rowoff-xs, xs | xe<<16}
-  int* flags = reinterpret_cast<int*>(smem + sp.flag_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);   // one mbarrier per band (TMA)
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63
   float qx = 0.f, qy = 0.f;
@@ -210,26 +283,43 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     gmap_b = p.gmap + (size_t)b * G * G * C + c0;
   }
 
-  // cp.async band k of the caller's map window into its ring rows; cells outside the map are zero-filled
+  // Band k of the caller's map window -> its ring rows; cells outside the map arrive as zeros.
   auto prefetch_band = [&](int k) {
-    for (int t = tid; t < BAND * WW; t += NT) {
-      int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
-      if (uu < WW) {
-        int u = u0 + uu, v = v0 + vv;
-        bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
-        const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
-        F4* dst = ring + 1 + ((uu + S0) % RR) * WW + vv;
-        if (VEC) {
-          async_copy16(dst, src, inside);
-        } else {
-#pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch) async_copy4(&dst->v[ch], src + (ch < nch ? ch : 0), inside && ch < nch);
+    if (TMA) {
+      if (tid == 0) {
+        const int rows = (k + 1) * BAND <= WW ? BAND : WW - k * BAND;
+        mbar_expect_tx(&bars[k], (unsigned)(rows * WW * 16));
+        for (int r = 0; r < rows; ++r) {
+          const int uu = k * BAND + r;
+          tma_load_row(ring + 1 + ((uu + S0) % RR) * WWP, &p.tmap, c0, v0, u0 + uu, b, &bars[k]);
         }
       }
+    } else {
+      for (int t = tid; t < BAND * WW; t += NT) {
+        int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
+        if (uu < WW) {
+          int u = u0 + uu, v = v0 + vv;
+          bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
+          const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
+          F4* dst = ring + 1 + ((uu + S0) % RR) * WWP + vv;
+          if (VEC) {
+            async_copy16(dst, src, inside);
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < SLAB; ++ch) async_copy4(&dst->v[ch], src + (ch < nch ? ch : 0), inside && ch < nch);
+          }
+        }
+      }
+      async_commit();
     }
-    async_commit();
   };
-  if (!p.stop_after_scatter) prefetch_band(0);     // streams in underneath the scatter (slots beyond the key planes)
+  if (!p.stop_after_scatter) {
+    if (TMA && tid == 0) {
+      for (int k = 0; k < NB; ++k) mbar_init(&bars[k], 1);
+      mbar_init_fence();
+    }
+    prefetch_band(0);              // streams in underneath the scatter (slots beyond the key planes)
+  }
 
   // ---- tables ------------------------------------------------------------------------------
   for (int t = tid; t < E; t += NT) baseE[t] = base_coord(t, E);
@@ -243,7 +333,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
     fanrow[t] = fr;
   }
-  if (tid == 0) { flags[0] = 0; X[0] = f4_zero(); Pf[0] = f4_zero(); }
+  if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); }
   for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = 0u;
   WSMG_SYNC();
 
@@ -252,7 +342,6 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
     const float* plane0 = p.feat + ((size_t)b * C + c0) * HW;
     const int n4 = HW / 4;
-    int saw_invalid = 0;
     for (int t = tid; t < n4; t += 2 * NT) {
       // two 4-pixel groups per trip so that 8 feature loads are in flight per thread
       uint2 cc[2];
@@ -264,19 +353,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         cc[h].x = cc[h].y = 0xFFFFFFFFu;
         if (tt < n4) cc[h] = ld_codes(codes4 + tt);
       }
-      uint32_t code[2][4];
-      bool ok[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int tt = t + h * NT;
-        code[h][0] = cc[h].x & 0xFFFFu; code[h][1] = cc[h].x >> 16;
-        code[h][2] = cc[h].y & 0xFFFFu; code[h][3] = cc[h].y >> 16;
-#pragma unroll
-        for (int px = 0; px < 4; ++px) ok[h][px] = code[h][px] < CODE_OUTLIER;   // valid pixels carry a fan cell
-        const bool any_ok = ok[h][0] || ok[h][1] || ok[h][2] || ok[h][3];
-        const bool all_ok = ok[h][0] && ok[h][1] && ok[h][2] && ok[h][3];
-        if (tt < n4 && !all_ok) saw_invalid = 1;
-        live[h] = tt < n4 && any_ok;                 // a group where no pixel writes skips its feature read
+        // valid pixels carry a fan cell (< CODE_OUTLIER): every u16 lane of (x & y) has its top 15
+        // bits set iff none of the four pixels writes -- such a group skips its feature read.
+        live[h] = ((cc[h].x & cc[h].y) | 0x00010001u) != 0xFFFFFFFFu;      // (codes past the end were set to 0xFFFF)
         const float* src = plane0 + 4 * (size_t)tt;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
@@ -285,36 +367,41 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (!live[h]) continue;
-        // runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
-        // finish_cell() turns -0 into +0 like the reference): one shared-memory atomic per run.
-        // Per value: select, max, 2-op key, predicated ATOMS, select -- no branches.
-        bool flush[4], last[3];
-        last[0] = code[h][1] != code[h][0]; last[1] = code[h][2] != code[h][1]; last[2] = code[h][3] != code[h][2];
-        flush[0] = ok[h][0] && last[0]; flush[1] = ok[h][1] && last[1]; flush[2] = ok[h][2] && last[2]; flush[3] = ok[h][3];
-        uint32_t* cell[4];
+        // Runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
+        // finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
+        // channel.  A pixel that does not write never flushes and is always followed by a reset before
+        // the next flush, so its value needs no masking.
+        unsigned code[5];
+        code[0] = cc[h].x & 0xFFFFu; code[1] = cc[h].x >> 16;
+        code[2] = cc[h].y & 0xFFFFu; code[3] = cc[h].y >> 16; code[4] = 0xFFFFFFFFu;
+        float run[SLAB];
 #pragma unroll
-        for (int px = 0; px < 4; ++px) cell[px] = Pk + (ok[h][px] ? code[h][px] : 0u);
+        for (int ch = 0; ch < SLAB; ++ch) run[ch] = -INFINITY;
 #pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch) {
-          if (ch >= nch) break;
-          float run = -INFINITY;
+        for (int px = 0; px < 4; ++px) {
 #pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            run = fmaxf(run, ok[h][px] ? f[h][ch].v[px] : -INFINITY);
-            if (flush[px]) smem_max(cell[px] + ch * npp, f2key(run));
-            if (px < 3) run = last[px] ? -INFINITY : run;
+          for (int ch = 0; ch < SLAB; ++ch) run[ch] = fmaxf(run[ch], f[h][ch].v[px]);
+          uint32_t* cell = Pk + (code[px] < CODE_OUTLIER ? code[px] : 0u);
+          if (VEC) {
+            red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
+          } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
+            for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
+          }
+          if (px < 3) {
+            const bool last = code[px + 1] != code[px];
+#pragma unroll
+            for (int ch = 0; ch < SLAB; ++ch) run[ch] = last ? -INFINITY : run[ch];
           }
         }
       }
     }
-    if (saw_invalid) flags[0] = 1;      // same value from every writer
   }
   WSMG_SYNC();
 
   // ---- phase 1b: keys -> finished floats, planar -> F4 per cell (rgb_mapping.py:228-230) -----
   if (p.proj_in == nullptr) {
     const uint32_t sentinel_key = f2key(SENTINEL);
-    const bool inv = flags[0] != 0;
+    const bool inv = (p.env_flags[b] & 1u) != 0;
     for (int t = tid; t < fan_cells; t += NT) {
       F4 v;
 #pragma unroll
@@ -381,9 +468,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 
   // ---- phase 3 tables: the two (separable) translations (rgb_mapping.py:45-53, 57-65) ----------
   // colT[vv] = {x0 | NEG, x0+1 | NEG, bits(wx), column inside the map}
-  // rowT[uu] = {1 + y0*E | NEG, 1 + (y0+1)*E | NEG, bits(wy), 1 + slot(uu)*WW if the row is inside the map else NEG}
+  // rowT[uu] = {1 + y0*E | NEG, 1 + (y0+1)*E | NEG, bits(wy), 1 + slot(uu)*WWP if the row is inside the map else NEG}
   // bXT[q]   = {col0 | NEG, col1 | NEG, bits(wx), 0}
-  // bYT[p]   = {1 + slot(row0)*WW | NEG, 1 + slot(row1)*WW | NEG, bits(wy), 0}       (slot(r) = (r + S0) % RR)
+  // bYT[p]   = {1 + slot(row0)*WWP | NEG, 1 + slot(row1)*WWP | NEG, bits(wy), 0}     (slot(r) = (r + S0) % RR)
   for (int t = tid; t < WW; t += NT) {
     int v = v0 + t, u = u0 + t;
     I4 ct; ct.a = ct.b = NEG; ct.c = 0; ct.d = 0;
@@ -401,7 +488,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       int y0 = tp.i0 - paste_lo;
       rt.a = (unsigned)y0 < (unsigned)E ? 1 + y0 * E : NEG;
       rt.b = (unsigned)(y0 + 1) < (unsigned)E ? 1 + (y0 + 1) * E : NEG;
-      rt.c = as_int(tp.w1); rt.d = 1 + ((t + S0) % RR) * WW;
+      rt.c = as_int(tp.w1); rt.d = 1 + ((t + S0) % RR) * WWP;
     }
     rowT[t] = rt;
   }
@@ -413,11 +500,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     bXT[t] = bx;
     Tap1D tq = make_tap(unnormalize(base_coord(t + paste_lo, G) + qy, half_g));
     int ry = tq.i0 - u0;
-    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + ((ry + S0) % RR) * WW : NEG;
-    by.b = (unsigned)(ry + 1) < (unsigned)WW ? 1 + ((ry + 1 + S0) % RR) * WW : NEG;
+    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + ((ry + S0) % RR) * WWP : NEG;
+    by.b = (unsigned)(ry + 1) < (unsigned)WW ? 1 + ((ry + 1 + S0) % RR) * WWP : NEG;
     by.c = as_int(tq.w1); by.d = 0;
     bYT[t] = by;
   }
+  if (TMA) fence_proxy_async();    // generic writes to the key planes precede TMA writes to the same bytes
   WSMG_SYNC();                     // R complete, fan dead: the key planes may now be overwritten by ring rows
   if (NB > 1) prefetch_band(1);
 
@@ -428,11 +516,29 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   int p_lo = 0;
   for (int k = 0; k <= NB; ++k) {
     if (k < NB) {
-      if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
+      if (TMA) mbar_wait(&bars[k], 0);
+      else if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
     }
     WSMG_SYNC();
-    if (k + 2 < NB) prefetch_band(k + 2);
-    else async_commit();                                    // keep one group per trip so wait<1> stays exact
+    if (TMA) {
+      if (tid == 0) {
+        if (k >= 1) {              // band k-1 is final in shared memory (fenced + barrier): store it
+          const int kb = k - 1, rows = (kb + 1) * BAND <= WW ? BAND : WW - kb * BAND;
+          for (int r = 0; r < rows; ++r) {
+            const int uu = kb * BAND + r;
+            tma_store_row(&p.tmap, c0, v0, u0 + uu, b, ring + 1 + ((uu + S0) % RR) * WWP);
+          }
+          tma_commit();
+        }
+        if (k + 2 < NB) {
+          tma_wait_read<1>();      // stores older than the one just committed have read their rows: slots are free
+          prefetch_band(k + 2);
+        }
+      }
+    } else {
+      if (k + 2 < NB) prefetch_band(k + 2);
+      else async_commit();         // keep one group per trip so wait<1> stays exact
+    }
     if (k < NB) {
       for (int t = tid; t < BAND * WW; t += NT) {
         int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
@@ -447,16 +553,19 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #pragma unroll
           for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(f.v[ch], tv.v[ch]);
           *cellp = f;
-          float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
-          if (VEC) {
-            *reinterpret_cast<F4*>(dst) = f;
-          } else {
+          if (!TMA) {
+            float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
+            if (VEC) {
+              *reinterpret_cast<F4*>(dst) = f;
+            } else {
 #pragma unroll
-            for (int ch = 0; ch < SLAB; ++ch)
-              if (ch < nch) dst[ch] = f.v[ch];
+              for (int ch = 0; ch < SLAB; ++ch)
+                if (ch < nch) dst[ch] = f.v[ch];
+            }
           }
         }
       }
+      if (TMA) fence_proxy_async();     // make the fused rows visible to the TMA store issued after the next barrier
     }
     if (k >= 1) {
       int done = k * BAND < WW ? k * BAND : WW;            // F rows finished before this trip
@@ -492,6 +601,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     for (int ch = 0; ch < SLAB; ++ch)
       if (ch < nch) st_stream(ego_b + (size_t)ch * EE + t, r.v[ch]);
   }
+  if (TMA && tid == 0) tma_wait_read<0>();   // the last band's store must have read its rows before the CTA retires
 }
 
 }  // namespace wsmg

@@ -19,7 +19,8 @@ using namespace wsmg;
 
 extern "C" {
 
-int wsmg_emul_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid, uint16_t* codes, const wsmg_dims* d) {
+int wsmg_emul_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid, uint16_t* codes, uint32_t* env_flags,
+                              const wsmg_dims* d) {
   int rc = validate_dims(d);
   if (rc) return rc;
   const Geo g = make_geo(d);
@@ -30,6 +31,7 @@ int wsmg_emul_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid
     for (int t = 0; t < HW; ++t) {
       int i = t / g.Wf, j = t - i * g.Wf, x, y;
       bool ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
+      if (env_flags && !ok) env_flags[b] |= 1u;
       if (codes) {
         uint16_t code = CODE_INVALID;
         if (ok) {
@@ -56,7 +58,8 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
   const char* force = getenv("WSMG_FORCE_GENERIC");
   const bool generic = force && force[0] == '1';
   std::vector<uint16_t> codes((size_t)d->bs * HW);
-  if (mode != 2) wsmg_emul_unproject_index(depth, nullptr, nullptr, codes.data(), d);
+  std::vector<uint32_t> flags(d->bs, 0u);
+  if (mode != 2) wsmg_emul_unproject_index(depth, nullptr, nullptr, codes.data(), flags.data(), d);
   if (mode != 1) {
     const size_t per_env = (size_t)g.G * g.G * g.C;
     for (int b = 0; b < d->bs; ++b) {
@@ -66,17 +69,17 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
     }
   }
   FusedParams p{};
-  p.feat = feat; p.codes = codes.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
+  p.feat = feat; p.codes = codes.data(); p.env_flags = flags.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
   p.ego = ego_out; p.proj_out = proj_out; p.proj_in = (mode == 2) ? proj_in : nullptr;
   p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g; p.sp = sp;
-  std::vector<unsigned char> smem(sp.total + 16);
-  unsigned char* sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+  std::vector<unsigned char> smem(sp.total + 128);
+  unsigned char* sm = smem.data() + ((128 - ((uintptr_t)smem.data() & 127)) & 127);
   const int slabs = (g.C + SLAB - 1) / SLAB;
   for (int blk = 0; blk < d->bs * slabs; ++blk) {
     memset(sm, 0xCD, sp.total);     // poison: nothing may rely on zeroed shared memory
-    if (g.C % 4 == 0 && g.E == 100 && g.G == 240 && HW == 224 * 224 && !generic) fused_body<1, 100, 240, 224 * 224, true>(p, blk, sm, 0);
-    else if (g.C % 4 == 0) fused_body<1, 0, 0, 0, true>(p, blk, sm, 0);
-    else fused_body<1, 0, 0, 0, false>(p, blk, sm, 0);
+    if (g.C % 4 == 0 && g.E == 100 && g.G == 240 && HW == 224 * 224 && !generic) fused_body<1, 100, 240, 224 * 224, true, false>(p, blk, sm, 0);
+    else if (g.C % 4 == 0) fused_body<1, 0, 0, 0, true, false>(p, blk, sm, 0);
+    else fused_body<1, 0, 0, 0, false, false>(p, blk, sm, 0);
   }
   return 0;
 }

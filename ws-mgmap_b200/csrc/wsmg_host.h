@@ -63,10 +63,13 @@ inline const char* error_string(int code) {
   }
 }
 
-// scratch layout: [bs * Hf*Wf] uint16 packed cell codes
-inline size_t scratch_bytes(const wsmg_dims* d) {
+// scratch layout: [bs * Hf*Wf] uint16 packed cell codes | [bs] uint32 env flags
+inline size_t scratch_codes_bytes(const wsmg_dims* d) {
   size_t codes = (size_t)d->bs * d->Hf * d->Wf * sizeof(uint16_t);
   return (codes + 255) & ~(size_t)255;
+}
+inline size_t scratch_bytes(const wsmg_dims* d) {
+  return scratch_codes_bytes(d) + (((size_t)d->bs * sizeof(uint32_t) + 255) & ~(size_t)255);
 }
 
 inline void base_coords_host(float* out, int n) {
