@@ -233,7 +233,7 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 // at compile time (the reference's 100 / 240 / 224*224); 0: read from p.g.
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
 // TMA: the map window moves through cp.async.bulk.tensor (needs VEC); else cp.async + st.global.
-template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA>
+template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA_BUILD>
 WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, const int tid) {
   const Geo& g = p.g;
   const SmemPlan& sp = p.sp;
@@ -282,6 +282,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     v0 = (int)sx + paste_lo - 1;
     gmap_b = p.gmap + (size_t)b * G * G * C + c0;
   }
+  // TMA stores must not leave the tensor: a window clipped by the map border (agent within ~6 m of the
+  // edge of the 28.8 m map) takes the cp.async / st.global path instead.  CTA-uniform.
+  const bool TMA = TMA_BUILD && u0 >= 0 && v0 >= 0 && u0 + WW <= G && v0 + WW <= G;
 
   // Band k of the caller's map window -> its ring rows; cells outside the map arrive as zeros.
   auto prefetch_band = [&](int k) {
