@@ -51,42 +51,63 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
 }
 
 // ------------------------------------------------------------------ k_cells
-// One thread per sampled pixel of the Hf x Wf frame.  Writes the packed fan code the fused
-// kernel scatters with and/or the reference-shaped (linear index, invalid) pair of the stage API.
+// Fused unproject + height-band test + bin + index.  Each thread owns four consecutive sampled pixels
+// of the Hf x Wf frame (one 8-byte store of packed fan codes); the per-column pinhole term and source
+// column live in shared-memory tables built once per block, the per-row term is one division per
+// thread.  Also emits the reference-shaped (linear index, invalid) pair for the stage API and the
+// per-env "some pixel does not write" flag (those pixels send the sentinel to cell 0,
+// rgb_mapping.py:207-212).
+constexpr int CELLS_PX = 4;
+constexpr int CELLS_MAX_W = 1024;
 __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
                                                           int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
                                                           uint32_t* __restrict__ env_flags, Geo g) {
   __shared__ int rowoff[160];
+  __shared__ int col_src[CELLS_MAX_W];
+  __shared__ float col_xx[CELLS_MAX_W];
   for (int t = threadIdx.x; t < g.fan_rows; t += blockDim.x) {
     int off = 0;
     for (int y = 0; y < t; ++y) off += fan_row_width(y, g.E);
     rowoff[t] = off;
   }
+  for (int j = threadIdx.x; j < g.Wf; j += blockDim.x) {
+    int c = sample_index(g, j);
+    col_src[j] = c;
+    col_xx[j] = pinhole_xx(g, c);
+  }
   __syncthreads();
   const int b = blockIdx.y;
   const int HW = g.Hf * g.Wf;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = t < HW;
-  int x = 0, y = 0;
-  bool ok = true;
-  if (in_range) {
-    const int i = t / g.Wf, j = t - i * g.Wf;
-    ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
-  }
-  // invalid pixels write the sentinel to cell 0 (rgb_mapping.py:207-212): the fused kernel needs to know whether any exists
-  const unsigned any_bad = __ballot_sync(0xFFFFFFFFu, !ok);
-  if (env_flags != nullptr && any_bad != 0u && (threadIdx.x & 31) == 0) atomicOr(env_flags + b, 1u);
-  if (!in_range) return;
-  if (codes != nullptr) {
-    uint16_t code = CODE_INVALID;
-    if (ok) {
-      if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code = (uint16_t)(rowoff[y] + x - fan_x_lo(y));
-      else code = CODE_OUTLIER;
+  const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * CELLS_PX;
+  const float* depth_b = depth + (size_t)b * g.Hd * g.Wd;
+  int i = t0 / g.Wf, j = t0 - i * g.Wf;
+  int r = sample_index(g, i);
+  float yy = pinhole_yy(g, r);
+  uint32_t code[CELLS_PX];
+  bool any_bad = false;
+#pragma unroll
+  for (int px = 0; px < CELLS_PX; ++px) {
+    const int t = t0 + px;
+    code[px] = CODE_INVALID;
+    if (t < HW) {
+      int x, y;
+      const bool ok = unproject_depth(g, depth_b[(size_t)r * g.Wd + col_src[j]], col_xx[j], yy, &x, &y);
+      any_bad |= !ok;
+      if (ok) {
+        if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
+        else code[px] = CODE_OUTLIER;
+      }
+      if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
+      if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
+      if (++j == g.Wf) { j = 0; ++i; r = sample_index(g, i); yy = pinhole_yy(g, r); }
     }
-    codes[(size_t)b * HW + t] = code;
   }
-  if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
-  if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
+  if (codes != nullptr && t0 < HW) {       // HW % 4 == 0 (validated): the four codes are one aligned 8-byte word
+    uint2 w; w.x = code[0] | (code[1] << 16); w.y = code[2] | (code[3] << 16);
+    *reinterpret_cast<uint2*>(codes + (size_t)b * HW + t0) = w;
+  }
+  const unsigned bad = __ballot_sync(0xFFFFFFFFu, any_bad);
+  if (env_flags != nullptr && bad != 0u && (threadIdx.x & 31) == 0) atomicOr(env_flags + b, 1u);
 }
 
 // ------------------------------------------------------------------ k_fused
@@ -108,9 +129,10 @@ static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, con
 
 static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, uint32_t* env_flags,
                         const Geo& g, int bs, cudaStream_t s) {
-  if (g.fan_rows > 160) return WSMG_E_DIMS;
+  if (g.fan_rows > 160 || g.Wf > CELLS_MAX_W) return WSMG_E_DIMS;
   const int HW = g.Hf * g.Wf;
-  dim3 grid((HW + CELLS_THREADS - 1) / CELLS_THREADS, bs);
+  const int per_block = CELLS_THREADS * CELLS_PX;
+  dim3 grid((HW + per_block - 1) / per_block, bs);
   k_cells<<<grid, CELLS_THREADS, 0, s>>>(depth, codes, lin, invalid, env_flags, g);
   return (int)cudaGetLastError();
 }

@@ -30,7 +30,9 @@ int wsmg_emul_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid
   for (int b = 0; b < d->bs; ++b)
     for (int t = 0; t < HW; ++t) {
       int i = t / g.Wf, j = t - i * g.Wf, x, y;
-      bool ok = unproject_pixel(g, depth + (size_t)b * g.Hd * g.Wd, i, j, &x, &y);
+      // same split as k_cells: per-row / per-column pinhole terms, then the depth-dependent part
+      const int r = sample_index(g, i), c = sample_index(g, j);
+      bool ok = unproject_depth(g, depth[(size_t)b * g.Hd * g.Wd + (size_t)r * g.Wd + c], pinhole_xx(g, c), pinhole_yy(g, r), &x, &y);
       if (env_flags && !ok) env_flags[b] |= 1u;
       if (codes) {
         uint16_t code = CODE_INVALID;

@@ -121,6 +121,21 @@ WSMG_HD void gps_cell(const Geo& g, float gps0, float gps1, float* gxc, float* g
 // ComputeSpatialLocs.forward + validity/bounds of ProjectToGroundPlane.forward
 // (rgb_mapping.py:159-176, 188-204) for sampled pixel (i,j) of the Hf x Wf frame.
 // Returns true when the pixel writes; *x,*y are the ego cell.
+// Split form used by k_cells: the column term xx and the row term yy are per-column / per-row constants.
+WSMG_HD int sample_index(const Geo& g, int i) { return (int)((float)i * g.ksub); }          // rgb_mapping.py:192-193
+WSMG_HD float pinhole_xx(const Geo& g, int c) { return ((float)c - g.cx) / g.fx; }          // rgb_mapping.py:161
+WSMG_HD float pinhole_yy(const Geo& g, int r) { return ((float)(g.Hd - r) - g.cy) / g.fy; } // rgb_mapping.py:160,162
+WSMG_HD bool unproject_depth(const Geo& g, float depth01, float xx, float yy, int* x, int* y) {
+  float z = depth01 * 10.0f;                                  // rgb_mapping.py:37
+  float X = xx * z, Y = yy * z;
+  bool ok = (z != 0.0f) && (Y > -1.5f) && (Y < 0.1f);
+  float xf = rintf(X / g.cell + g.half);
+  float yf = rintf(-(z / g.cell) + g.half);
+  ok = ok && (xf >= 0.0f) && (xf < (float)g.E) && (yf >= 0.0f) && (yf < (float)g.E);
+  *x = ok ? (int)xf : 0;
+  *y = ok ? (int)yf : 0;
+  return ok;
+}
 WSMG_HD bool unproject_pixel(const Geo& g, const float* depth_b, int i, int j, int* x, int* y) {
   int r = (int)((float)i * g.ksub);
   int c = (int)((float)j * g.ksub);
