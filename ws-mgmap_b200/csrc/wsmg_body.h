@@ -287,13 +287,19 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   const bool TMA = TMA_BUILD && u0 >= 0 && v0 >= 0 && u0 + WW <= G && v0 + WW <= G;
 
   // Band k of the caller's map window -> its ring rows; cells outside the map arrive as zeros.
+  // TMA: issued by the first BAND lanes of the last warp (it owns no window / crop cell), one row each.
+  const int tma_lane = tid - (NT - 32);                     // 0..31 in the TMA warp, negative elsewhere
+  auto tma_rows = [&](int k) { return (k + 1) * BAND <= WW ? BAND : WW - k * BAND; };
   auto prefetch_band = [&](int k) {
     if (TMA) {
-      if (tid == 0) {
-        const int rows = (k + 1) * BAND <= WW ? BAND : WW - k * BAND;
-        mbar_expect_tx(&bars[k], (unsigned)(rows * WW * 16));
-        for (int r = 0; r < rows; ++r) {
-          const int uu = k * BAND + r;
+      if (tma_lane >= 0) {
+        const int rows = tma_rows(k);
+        if (tma_lane == 0) mbar_expect_tx(&bars[k], (unsigned)(rows * WW * 16));
+#if defined(__CUDACC__)
+        __syncwarp();
+#endif
+        if (tma_lane < rows) {
+          const int uu = k * BAND + tma_lane;
           tma_load_row(ring + 1 + ((uu + S0) % RR) * WWP, &p.tmap, c0, v0, u0 + uu, b, &bars[k]);
         }
       }
@@ -317,9 +323,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
   };
   if (!p.stop_after_scatter) {
-    if (TMA && tid == 0) {
-      for (int k = 0; k < NB; ++k) mbar_init(&bars[k], 1);
-      mbar_init_fence();
+    if (TMA && tma_lane >= 0) {
+      if (tma_lane == 0) {
+        for (int k = 0; k < NB; ++k) mbar_init(&bars[k], 1);
+        mbar_init_fence();
+      }
+#if defined(__CUDACC__)
+      __syncwarp();
+#endif
     }
     prefetch_band(0);              // streams in underneath the scatter (slots beyond the key planes)
   }
@@ -345,6 +356,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
     const float* plane0 = p.feat + ((size_t)b * C + c0) * HW;
     const int n4 = HW / 4;
+    // codes of the first trip; inside the loop the next trip's codes are requested before this trip's
+    // features are consumed, so the L2 latency of the codes never sits in front of the feature loads
+    uint2 nxt[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      nxt[h].x = nxt[h].y = 0xFFFFFFFFu;
+      if (tid + h * NT < n4) nxt[h] = ld_codes(codes4 + tid + h * NT);
+    }
     for (int t = tid; t < n4; t += 2 * NT) {
       // two 4-pixel groups per trip so that 8 feature loads are in flight per thread
       uint2 cc[2];
@@ -352,9 +371,10 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       F4 f[2][SLAB];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int tt = t + h * NT;
-        cc[h].x = cc[h].y = 0xFFFFFFFFu;
-        if (tt < n4) cc[h] = ld_codes(codes4 + tt);
+        cc[h] = nxt[h];
+        const int tn = t + 2 * NT + h * NT;
+        nxt[h].x = nxt[h].y = 0xFFFFFFFFu;
+        if (tn < n4) nxt[h] = ld_codes(codes4 + tn);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -517,70 +537,76 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // the crop rows whose F rows were finished by trip k-1: B row p reads F rows p..p+2 and overwrites
   // X row p, which only F rows p..p+2 read -- so rows p <= done-3 are safe.  One barrier per trip.
   int p_lo = 0;
+  auto fuse_band = [&](int k) {                              // 3a: F rows of band k, in place in the ring
+    for (int t = tid; t < BAND * WW; t += NT) {
+      int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
+      if (uu >= WW) continue;
+      const I4 ct = colT[vv], rt = rowT[uu];
+      if (ct.d > 0 && rt.d > 0) {
+        Weights w = make_weights(as_float(ct.c), as_float(rt.c));
+        F4 a = X[imax0(rt.a + ct.a)], bb = X[imax0(rt.a + ct.b)], c = X[imax0(rt.b + ct.a)], d = X[imax0(rt.b + ct.b)];
+        F4 tv = blend_f4(a, bb, c, d, w);
+        F4* cellp = ring + rt.d + vv;
+        F4 f = *cellp;
+#pragma unroll
+        for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(f.v[ch], tv.v[ch]);
+        *cellp = f;
+        if (!TMA) {
+          float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
+          if (VEC) {
+            *reinterpret_cast<F4*>(dst) = f;
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < SLAB; ++ch)
+              if (ch < nch) dst[ch] = f.v[ch];
+          }
+        }
+      }
+    }
+  };
+  auto crop_rows = [&](int k) {                              // 3b: B rows whose F rows were finished before trip k
+    int done = k * BAND < WW ? k * BAND : WW;
+    int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
+    for (int t = tid; t < (p_hi - p_lo) * E; t += NT) {
+      int dr = t / E, q = t - dr * E, pr = p_lo + dr;
+      const I4 bx = bXT[q], by = bYT[pr];
+      Weights w = make_weights(as_float(bx.c), as_float(by.c));
+      F4 a = ring[imax0(by.a + bx.a)], bb = ring[imax0(by.a + bx.b)], c = ring[imax0(by.b + bx.a)], d = ring[imax0(by.b + bx.b)];
+      X[1 + pr * E + q] = blend_f4(a, bb, c, d, w);
+    }
+    p_lo = p_hi;
+  };
   for (int k = 0; k <= NB; ++k) {
-    if (k < NB) {
-      if (TMA) mbar_wait(&bars[k], 0);
-      else if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
+    if (!TMA && k < NB) {
+      if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
     }
     WSMG_SYNC();
     if (TMA) {
-      if (tid == 0) {
-        if (k >= 1) {              // band k-1 is final in shared memory (fenced + barrier): store it
-          const int kb = k - 1, rows = (kb + 1) * BAND <= WW ? BAND : WW - kb * BAND;
-          for (int r = 0; r < rows; ++r) {
-            const int uu = kb * BAND + r;
+      if (tma_lane >= 0) {
+        if (k >= 1) {              // band k-1 is final in shared memory (fenced + barrier): store it, one row per lane
+          const int kb = k - 1;
+          if (tma_lane < tma_rows(kb)) {
+            const int uu = kb * BAND + tma_lane;
             tma_store_row(&p.tmap, c0, v0, u0 + uu, b, ring + 1 + ((uu + S0) % RR) * WWP);
           }
           tma_commit();
         }
         if (k + 2 < NB) {
-          tma_wait_read<1>();      // stores older than the one just committed have read their rows: slots are free
-          prefetch_band(k + 2);
+          tma_wait_read<1>();      // every lane: its stores older than the one just committed have read their rows
+          prefetch_band(k + 2);    // (__syncwarp inside orders all lanes' waits before any load is issued)
         }
+      }
+      if (k >= 1) crop_rows(k);    // needs only finished F rows: runs while band k is still landing
+      if (k < NB) {
+        mbar_wait(&bars[k], 0);
+        fuse_band(k);
+        fence_proxy_async();       // make the fused rows visible to the TMA store issued after the next barrier
       }
     } else {
       if (k + 2 < NB) prefetch_band(k + 2);
       else async_commit();         // keep one group per trip so wait<1> stays exact
-    }
-    if (k < NB) {
-      for (int t = tid; t < BAND * WW; t += NT) {
-        int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
-        if (uu >= WW) continue;
-        const I4 ct = colT[vv], rt = rowT[uu];
-        if (ct.d > 0 && rt.d > 0) {
-          Weights w = make_weights(as_float(ct.c), as_float(rt.c));
-          F4 a = X[imax0(rt.a + ct.a)], bb = X[imax0(rt.a + ct.b)], c = X[imax0(rt.b + ct.a)], d = X[imax0(rt.b + ct.b)];
-          F4 tv = blend_f4(a, bb, c, d, w);
-          F4* cellp = ring + rt.d + vv;
-          F4 f = *cellp;
-#pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(f.v[ch], tv.v[ch]);
-          *cellp = f;
-          if (!TMA) {
-            float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
-            if (VEC) {
-              *reinterpret_cast<F4*>(dst) = f;
-            } else {
-#pragma unroll
-              for (int ch = 0; ch < SLAB; ++ch)
-                if (ch < nch) dst[ch] = f.v[ch];
-            }
-          }
-        }
-      }
-      if (TMA) fence_proxy_async();     // make the fused rows visible to the TMA store issued after the next barrier
-    }
-    if (k >= 1) {
-      int done = k * BAND < WW ? k * BAND : WW;            // F rows finished before this trip
-      int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
-      for (int t = tid; t < (p_hi - p_lo) * E; t += NT) {
-        int dr = t / E, q = t - dr * E, pr = p_lo + dr;
-        const I4 bx = bXT[q], by = bYT[pr];
-        Weights w = make_weights(as_float(bx.c), as_float(by.c));
-        F4 a = ring[imax0(by.a + bx.a)], bb = ring[imax0(by.a + bx.b)], c = ring[imax0(by.b + bx.a)], d = ring[imax0(by.b + bx.b)];
-        X[1 + pr * E + q] = blend_f4(a, bb, c, d, w);
-      }
-      p_lo = p_hi;
+      if (k < NB) fuse_band(k);
+      if (k >= 1) crop_rows(k);
     }
   }
   WSMG_SYNC();
@@ -604,7 +630,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     for (int ch = 0; ch < SLAB; ++ch)
       if (ch < nch) st_stream(ego_b + (size_t)ch * EE + t, r.v[ch]);
   }
-  if (TMA && tid == 0) tma_wait_read<0>();   // the last band's store must have read its rows before the CTA retires
+  if (TMA && tma_lane >= 0) tma_wait_read<0>();   // the last band's stores must have read their rows before the CTA retires
 }
 
 }  // namespace wsmg
