@@ -221,6 +221,10 @@ inline void red_max4(uint32_t* cell, int npp, unsigned code, unsigned next, uint
 }
 #endif
 
+// Tap that skips the shared-memory read when the index says "zero cell" (out of range, or a tap whose
+// bilinear weight is exactly 0 -- its product is an exact 0, so dropping the load is bit-exact for finite data).
+WSMG_HD F4 tap(const F4* base, int idx) { return idx > 0 ? base[idx] : f4_zero(); }
+
 WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const Weights& w) {
   F4 r;
 #pragma unroll
@@ -484,25 +488,26 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     int y0 = ty.i0, y1 = ty.i0 + 1;
     I2 r0 = fanrow[(unsigned)y0 < (unsigned)E ? y0 : E];
     I2 r1 = fanrow[(unsigned)y1 < (unsigned)E ? y1 : E];
-    F4 a = Pf[fan_idx(r0, tx.i0)], bb = Pf[fan_idx(r0, tx.i0 + 1)];
-    F4 c = Pf[fan_idx(r1, tx.i0)], d = Pf[fan_idx(r1, tx.i0 + 1)];
+    F4 a = tap(Pf, fan_idx(r0, tx.i0)), bb = tap(Pf, fan_idx(r0, tx.i0 + 1));     // ~70 % of the rotated grid lies outside the fan
+    F4 c = tap(Pf, fan_idx(r1, tx.i0)), d = tap(Pf, fan_idx(r1, tx.i0 + 1));
     X[1 + t] = blend_f4(a, bb, c, d, w);
   }
 
   // ---- phase 3 tables: the two (separable) translations (rgb_mapping.py:45-53, 57-65) ----------
-  // colT[vv] = {x0 | NEG, x0+1 | NEG, bits(wx), column inside the map}
+  // (NEG also marks a second tap whose weight is exactly 0 -- two thirds of the rows / columns)
+  // colT[vv] = {x0 | NEG, x0+1 | NEG, bits(wx), 0 if the column is inside the map else NEG}
   // rowT[uu] = {1 + y0*E | NEG, 1 + (y0+1)*E | NEG, bits(wy), 1 + slot(uu)*WWP if the row is inside the map else NEG}
   // bXT[q]   = {col0 | NEG, col1 | NEG, bits(wx), 0}
   // bYT[p]   = {1 + slot(row0)*WWP | NEG, 1 + slot(row1)*WWP | NEG, bits(wy), 0}     (slot(r) = (r + S0) % RR)
   for (int t = tid; t < WW; t += NT) {
     int v = v0 + t, u = u0 + t;
-    I4 ct; ct.a = ct.b = NEG; ct.c = 0; ct.d = 0;
+    I4 ct; ct.a = ct.b = NEG; ct.c = 0; ct.d = NEG;
     if ((unsigned)v < (unsigned)G) {    // canvas column sampled by global column v, relative to the pasted ego grid
       Tap1D tp = make_tap(unnormalize(base_coord(v, G) + (-qx), half_g));
       int x0 = tp.i0 - paste_lo;
       ct.a = (unsigned)x0 < (unsigned)E ? x0 : NEG;
-      ct.b = (unsigned)(x0 + 1) < (unsigned)E ? x0 + 1 : NEG;
-      ct.c = as_int(tp.w1); ct.d = 1;
+      ct.b = ((unsigned)(x0 + 1) < (unsigned)E && tp.w1 != 0.0f) ? x0 + 1 : NEG;     // weight exactly 0: skip the tap
+      ct.c = as_int(tp.w1); ct.d = 0;
     }
     colT[t] = ct;
     I4 rt; rt.a = rt.b = NEG; rt.c = 0; rt.d = NEG;
@@ -510,7 +515,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       Tap1D tp = make_tap(unnormalize(base_coord(u, G) + (-qy), half_g));
       int y0 = tp.i0 - paste_lo;
       rt.a = (unsigned)y0 < (unsigned)E ? 1 + y0 * E : NEG;
-      rt.b = (unsigned)(y0 + 1) < (unsigned)E ? 1 + (y0 + 1) * E : NEG;
+      rt.b = ((unsigned)(y0 + 1) < (unsigned)E && tp.w1 != 0.0f) ? 1 + (y0 + 1) * E : NEG;
       rt.c = as_int(tp.w1); rt.d = 1 + ((t + S0) % RR) * WWP;
     }
     rowT[t] = rt;
@@ -518,13 +523,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   for (int t = tid; t < E; t += NT) {   // global column / row sampled by crop cell t, relative to the window
     Tap1D tp = make_tap(unnormalize(base_coord(t + paste_lo, G) + qx, half_g));
     int cx = tp.i0 - v0;
-    I4 bx; bx.a = (unsigned)cx < (unsigned)WW ? cx : NEG; bx.b = (unsigned)(cx + 1) < (unsigned)WW ? cx + 1 : NEG;
+    I4 bx; bx.a = (unsigned)cx < (unsigned)WW ? cx : NEG;
+    bx.b = ((unsigned)(cx + 1) < (unsigned)WW && tp.w1 != 0.0f) ? cx + 1 : NEG;
     bx.c = as_int(tp.w1); bx.d = 0;
     bXT[t] = bx;
     Tap1D tq = make_tap(unnormalize(base_coord(t + paste_lo, G) + qy, half_g));
     int ry = tq.i0 - u0;
     I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + ((ry + S0) % RR) * WWP : NEG;
-    by.b = (unsigned)(ry + 1) < (unsigned)WW ? 1 + ((ry + 1 + S0) % RR) * WWP : NEG;
+    by.b = ((unsigned)(ry + 1) < (unsigned)WW && tq.w1 != 0.0f) ? 1 + ((ry + 1 + S0) % RR) * WWP : NEG;
     by.c = as_int(tq.w1); by.d = 0;
     bYT[t] = by;
   }
@@ -542,11 +548,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
       if (uu >= WW) continue;
       const I4 ct = colT[vv], rt = rowT[uu];
-      if (ct.d > 0 && rt.d > 0) {
+      const int cell = rt.d + ct.d + vv;                      // negative unless row and column are inside the map
+      if (cell > 0) {
         Weights w = make_weights(as_float(ct.c), as_float(rt.c));
-        F4 a = X[imax0(rt.a + ct.a)], bb = X[imax0(rt.a + ct.b)], c = X[imax0(rt.b + ct.a)], d = X[imax0(rt.b + ct.b)];
+        F4 a = tap(X, rt.a + ct.a), bb = tap(X, rt.a + ct.b), c = tap(X, rt.b + ct.a), d = tap(X, rt.b + ct.b);
         F4 tv = blend_f4(a, bb, c, d, w);
-        F4* cellp = ring + rt.d + vv;
+        F4* cellp = ring + cell;
         F4 f = *cellp;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(f.v[ch], tv.v[ch]);
@@ -571,7 +578,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       int dr = t / E, q = t - dr * E, pr = p_lo + dr;
       const I4 bx = bXT[q], by = bYT[pr];
       Weights w = make_weights(as_float(bx.c), as_float(by.c));
-      F4 a = ring[imax0(by.a + bx.a)], bb = ring[imax0(by.a + bx.b)], c = ring[imax0(by.b + bx.a)], d = ring[imax0(by.b + bx.b)];
+      F4 a = tap(ring, by.a + bx.a), bb = tap(ring, by.a + bx.b), c = tap(ring, by.b + bx.a), d = tap(ring, by.b + bx.b);
       X[1 + pr * E + q] = blend_f4(a, bb, c, d, w);
     }
     p_lo = p_hi;
