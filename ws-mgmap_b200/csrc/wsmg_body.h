@@ -72,13 +72,13 @@ constexpr int fan_cells_of(int E) {
 constexpr int npp_of(int fan_cells) { return (fan_cells + 3) & ~3; }
 
 struct SmemPlan {
-  int x_off, z_off, r2_off, tab_off, base_off, fanrow_off, bar_off, total;
+  int x_off, z_off, r2_off, tab_off, base_off, fanrow_off, ext_off, bar_off, total;
   int npp;        // words per key plane during the scatter
   int rr;         // ring rows
   int s0;         // ring slot of window row 0 (first slot beyond the key planes)
   int wwp;        // ring row stride in cells (row bytes are a multiple of 128 for TMA)
 };
-constexpr int MAX_BANDS = 32;
+constexpr int MAX_BANDS = 16;
 
 WSMG_HD int align16(int x) { return (x + 15) & ~15; }
 
@@ -99,7 +99,8 @@ WSMG_HD SmemPlan make_plan(const Geo& g) {
   s.tab_off = s.r2_off + s.rr * s.wwp * 16;
   s.base_off = s.tab_off + (2 * WW + 2 * g.E) * 16;
   s.fanrow_off = s.base_off + align16(g.E * 4);
-  s.bar_off = s.fanrow_off + align16((g.E + 1) * 8);
+  s.ext_off = s.fanrow_off + align16((g.E + 2) * 8);         // fanrow[E+1]; after the first rotation the same bytes hold rowE[E+2]
+  s.bar_off = s.ext_off + align16(g.E * 8);                  // ext[E]
   s.total = s.bar_off + MAX_BANDS * 8;
   return s;
 }
@@ -268,6 +269,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   I4* bYT = bXT + E;
   float* baseE = reinterpret_cast<float*>(smem + sp.base_off);
   I2* fanrow = reinterpret_cast<I2*>(smem + sp.fanrow_off);   // per grid row y (entry E = "no such row"): {1+rowoff-xs, xs | xe<<16}
+  I2* ext = reinterpret_cast<I2*>(smem + sp.ext_off);         // per R row: [first, last] column with a tap inside the fan
+  I2* rowE = fanrow;                                          // per window row: merged extent of its two source R rows (fanrow is dead by then)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);   // one mbarrier per band (TMA)
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63
@@ -352,6 +355,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     fanrow[t] = fr;
   }
   if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); }
+  for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
   for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = 0u;
   WSMG_SYNC();
 
@@ -479,23 +483,56 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float cs, sn;
   if (p.trig != nullptr) { cs = p.trig[4 * b + 0]; sn = p.trig[4 * b + 1]; }
   else { float h = -p.compass[b]; sn = sinf(h); cs = cosf(h); }
-  for (int t = tid; t < EE; t += NT) {
-    int i = t / E, j = t - i * E;
-    float ix, iy;
-    rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
-    Tap1D tx = make_tap(ix), ty = make_tap(iy);
-    Weights w = make_weights(tx.w1, ty.w1);
-    int y0 = ty.i0, y1 = ty.i0 + 1;
-    I2 r0 = fanrow[(unsigned)y0 < (unsigned)E ? y0 : E];
-    I2 r1 = fanrow[(unsigned)y1 < (unsigned)E ? y1 : E];
-    F4 a = tap(Pf, fan_idx(r0, tx.i0)), bb = tap(Pf, fan_idx(r0, tx.i0 + 1));     // ~70 % of the rotated grid lies outside the fan
-    F4 c = tap(Pf, fan_idx(r1, tx.i0)), d = tap(Pf, fan_idx(r1, tx.i0 + 1));
-    X[1 + t] = blend_f4(a, bb, c, d, w);
+  // Cells none of whose taps falls inside the fan (~70 % of the grid) are exact zeros: store and move on.
+  // The per-row extent of the other cells lets the fuse step skip window cells that only see zeros.
+  for (int t0 = 0; t0 < EE; t0 += NT) {
+    const int t = t0 + tid;
+    bool hit = false;
+    int i = 0, j = 0;
+    if (t < EE) {
+      i = t / E; j = t - i * E;
+      float ix, iy;
+      rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
+      Tap1D tx = make_tap(ix), ty = make_tap(iy);
+      int y0 = ty.i0, y1 = ty.i0 + 1;
+      I2 r0 = fanrow[(unsigned)y0 < (unsigned)E ? y0 : E];
+      I2 r1 = fanrow[(unsigned)y1 < (unsigned)E ? y1 : E];
+      const int ia = fan_idx(r0, tx.i0), ib = fan_idx(r0, tx.i0 + 1), ic = fan_idx(r1, tx.i0), id = fan_idx(r1, tx.i0 + 1);
+      hit = (ia | ib | ic | id) != 0;
+      if (hit) {
+        Weights w = make_weights(tx.w1, ty.w1);
+        X[1 + t] = blend_f4(tap(Pf, ia), tap(Pf, ib), tap(Pf, ic), tap(Pf, id), w);
+      } else {
+        X[1 + t] = f4_zero();
+      }
+    }
+#if defined(__CUDACC__)
+    // a warp covers 32 consecutive cells = at most two rows: one min/max pair per row segment
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m != 0u) {
+      const int lane = tid & 31;
+      const int t_first = t - lane, i_first = t_first / E, j_first = t_first - i_first * E;
+      const int split = E - j_first;                         // lanes >= split belong to the next row
+      const unsigned lo_mask = split >= 32 ? 0xFFFFFFFFu : ((1u << split) - 1u);
+      const unsigned m0 = m & lo_mask, m1 = m & ~lo_mask;
+      if (lane == 0 && m0 != 0u) {
+        atomicMin(&ext[i_first].a, j_first + __ffs(m0) - 1);
+        atomicMax(&ext[i_first].b, j_first + 31 - __clz(m0));
+      }
+      if (lane == 1 && m1 != 0u) {
+        atomicMin(&ext[i_first + 1].a, __ffs(m1) - 1 - split);
+        atomicMax(&ext[i_first + 1].b, 31 - __clz(m1) - split);
+      }
+    }
+#else
+    if (hit) { if (j < ext[i].a) ext[i].a = j; if (j > ext[i].b) ext[i].b = j; }
+#endif
   }
+  WSMG_SYNC();                     // extents complete
 
   // ---- phase 3 tables: the two (separable) translations (rgb_mapping.py:45-53, 57-65) ----------
   // (NEG also marks a second tap whose weight is exactly 0 -- two thirds of the rows / columns)
-  // colT[vv] = {x0 | NEG, x0+1 | NEG, bits(wx), 0 if the column is inside the map else NEG}
+  // colT[vv] = {x0 | NEG, x0+1 | NEG, bits(wx), NEG if the column is outside the map else (leftmost tap col) | (rightmost tap col + 1) << 10}
   // rowT[uu] = {1 + y0*E | NEG, 1 + (y0+1)*E | NEG, bits(wy), 1 + slot(uu)*WWP if the row is inside the map else NEG}
   // bXT[q]   = {col0 | NEG, col1 | NEG, bits(wx), 0}
   // bYT[p]   = {1 + slot(row0)*WWP | NEG, 1 + slot(row1)*WWP | NEG, bits(wy), 0}     (slot(r) = (r + S0) % RR)
@@ -507,7 +544,10 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       int x0 = tp.i0 - paste_lo;
       ct.a = (unsigned)x0 < (unsigned)E ? x0 : NEG;
       ct.b = ((unsigned)(x0 + 1) < (unsigned)E && tp.w1 != 0.0f) ? x0 + 1 : NEG;     // weight exactly 0: skip the tap
-      ct.c = as_int(tp.w1); ct.d = 0;
+      ct.c = as_int(tp.w1);
+      const int cl = ct.a >= 0 ? ct.a : (ct.b >= 0 ? ct.b : E + 1);     // leftmost / rightmost source column actually read
+      const int ch = ct.b >= 0 ? ct.b : ct.a;                           // (ct.a < 0 and ct.b < 0: none, ch + 1 <= 0)
+      ct.d = cl | ((ch >= 0 ? ch + 1 : 0) << 10);
     }
     colT[t] = ct;
     I4 rt; rt.a = rt.b = NEG; rt.c = 0; rt.d = NEG;
@@ -519,6 +559,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       rt.c = as_int(tp.w1); rt.d = 1 + ((t + S0) % RR) * WWP;
     }
     rowT[t] = rt;
+    {  // columns of R that can contribute to window row t: union of the extents of its (up to) two source rows
+      I2 e; e.a = E; e.b = -1;
+      if (rt.a > 0) { I2 s0e = ext[(rt.a - 1) / E]; e = s0e; }
+      if (rt.b > 0) { I2 s1e = ext[(rt.b - 1) / E]; e.a = s1e.a < e.a ? s1e.a : e.a; e.b = s1e.b > e.b ? s1e.b : e.b; }
+      rowE[t] = e;
+    }
   }
   for (int t = tid; t < E; t += NT) {   // global column / row sampled by crop cell t, relative to the window
     Tap1D tp = make_tap(unnormalize(base_coord(t + paste_lo, G) + qx, half_g));
@@ -548,8 +594,11 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
       if (uu >= WW) continue;
       const I4 ct = colT[vv], rt = rowT[uu];
-      const int cell = rt.d + ct.d + vv;                      // negative unless row and column are inside the map
-      if (cell > 0) {
+      const int cell = rt.d + vv;
+      const I2 e = rowE[uu];                                  // R columns that are not identically zero for this row
+      // row and column inside the map, and some tap column inside the extent; otherwise T == 0 and
+      // F = max(G, 0) = G: nothing to do
+      if (rt.d > 0 && ct.d >= 0 && (ct.d >> 10) > e.a && (ct.d & 1023) <= e.b) {
         Weights w = make_weights(as_float(ct.c), as_float(rt.c));
         F4 a = tap(X, rt.a + ct.a), bb = tap(X, rt.a + ct.b), c = tap(X, rt.b + ct.a), d = tap(X, rt.b + ct.b);
         F4 tv = blend_f4(a, bb, c, d, w);
