@@ -65,11 +65,7 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   __shared__ int rowoff[160];
   __shared__ int col_src[CELLS_MAX_W];
   __shared__ float col_xx[CELLS_MAX_W];
-  for (int t = threadIdx.x; t < g.fan_rows; t += blockDim.x) {
-    int off = 0;
-    for (int y = 0; y < t; ++y) off += fan_row_width(y, g.E);
-    rowoff[t] = off;
-  }
+  for (int t = threadIdx.x; t < g.fan_rows; t += blockDim.x) rowoff[t] = fan_row_offset(t, g.E);
   for (int j = threadIdx.x; j < g.Wf; j += blockDim.x) {
     int c = sample_index(g, j);
     col_src[j] = c;

@@ -347,10 +347,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   for (int t = tid; t <= E; t += NT) {
     I2 fr; fr.a = 0; fr.b = 1;                              // xs = 1 > xe = 0: empty row
     if (t < g.fan_rows) {
-      int off = 0;
-      for (int y = 0; y < t; ++y) off += fan_row_width(y, E);
       int xs = fan_x_lo(t), xe = fan_x_hi(t, E);
-      fr.a = 1 + off - xs; fr.b = xs | (xe << 16);
+      fr.a = 1 + fan_row_offset(t, E) - xs; fr.b = xs | (xe << 16);
     }
     fanrow[t] = fr;
   }
@@ -364,66 +362,71 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
     const float* plane0 = p.feat + ((size_t)b * C + c0) * HW;
     const int n4 = HW / 4;
-    // codes of the first trip; inside the loop the next trip's codes are requested before this trip's
-    // features are consumed, so the L2 latency of the codes never sits in front of the feature loads
-    uint2 nxt[2];
+    // Two slots (4-pixel groups tid + h*NT, stepping by 2*NT) rotate: as soon as a slot has been scattered its
+    // next group's feature loads are issued, so one group is always in flight while the other is reduced.
+    // Codes run one more step ahead (nxt), so their L2 latency never sits in front of the feature loads.
+    // Valid pixels carry a fan cell (< CODE_OUTLIER): every u16 lane of (x & y) has its top 15 bits set iff none of
+    // the four pixels writes -- such a group skips its feature read.
+    uint2 cc[2], nxt[2];
+    bool live[2];
+    F4 f[2][SLAB];
+    auto fetch_codes = [&](int tt) -> uint2 {
+      uint2 c; c.x = c.y = 0xFFFFFFFFu;
+      if (tt < n4) c = ld_codes(codes4 + tt);
+      return c;
+    };
+#pragma unroll
+    for (int h = 0; h < 2; ++h) cc[h] = fetch_codes(tid + h * NT);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      nxt[h].x = nxt[h].y = 0xFFFFFFFFu;
-      if (tid + h * NT < n4) nxt[h] = ld_codes(codes4 + tid + h * NT);
+      nxt[h] = fetch_codes(tid + (2 + h) * NT);
+      live[h] = ((cc[h].x & cc[h].y) | 0x00010001u) != 0xFFFFFFFFu;
+      const float* src = plane0 + 4 * (size_t)(tid + h * NT);
+#pragma unroll
+      for (int ch = 0; ch < SLAB; ++ch)
+        if (live[h] && ch < nch) f[h][ch] = ld_stream4(src + (size_t)ch * HW);
     }
     for (int t = tid; t < n4; t += 2 * NT) {
-      // two 4-pixel groups per trip so that 8 feature loads are in flight per thread
-      uint2 cc[2];
-      bool live[2];
-      F4 f[2][SLAB];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        cc[h] = nxt[h];
-        const int tn = t + 2 * NT + h * NT;
-        nxt[h].x = nxt[h].y = 0xFFFFFFFFu;
-        if (tn < n4) nxt[h] = ld_codes(codes4 + tn);
-      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int tt = t + h * NT;
-        // valid pixels carry a fan cell (< CODE_OUTLIER): every u16 lane of (x & y) has its top 15
-        // bits set iff none of the four pixels writes -- such a group skips its feature read.
-        live[h] = ((cc[h].x & cc[h].y) | 0x00010001u) != 0xFFFFFFFFu;      // (codes past the end were set to 0xFFFF)
-        const float* src = plane0 + 4 * (size_t)tt;
+        if (live[h]) {
+          // Runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
+          // finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
+          // channel.  A pixel that does not write never flushes and is always followed by a reset before
+          // the next flush, so its value needs no masking.
+          unsigned code[5];
+          code[0] = cc[h].x & 0xFFFFu; code[1] = cc[h].x >> 16;
+          code[2] = cc[h].y & 0xFFFFu; code[3] = cc[h].y >> 16; code[4] = 0xFFFFFFFFu;
+          float run[SLAB];
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch) run[ch] = -INFINITY;
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+#pragma unroll
+            for (int ch = 0; ch < SLAB; ++ch) run[ch] = fmaxf(run[ch], f[h][ch].v[px]);
+            uint32_t* cell = Pk + (code[px] < CODE_OUTLIER ? code[px] : 0u);
+            if (VEC) {
+              red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
+            } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
+              for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
+            }
+            if (px < 3) {
+              const bool last = code[px + 1] != code[px];
+#pragma unroll
+              for (int ch = 0; ch < SLAB; ++ch) run[ch] = last ? -INFINITY : run[ch];
+            }
+          }
+        }
+        // refill this slot with group tt + 2*NT
+        const int tn = tt + 2 * NT;
+        cc[h] = nxt[h];
+        live[h] = ((cc[h].x & cc[h].y) | 0x00010001u) != 0xFFFFFFFFu;      // (codes past the end are 0xFFFF)
+        const float* src = plane0 + 4 * (size_t)tn;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
           if (live[h] && ch < nch) f[h][ch] = ld_stream4(src + (size_t)ch * HW);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (!live[h]) continue;
-        // Runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
-        // finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
-        // channel.  A pixel that does not write never flushes and is always followed by a reset before
-        // the next flush, so its value needs no masking.
-        unsigned code[5];
-        code[0] = cc[h].x & 0xFFFFu; code[1] = cc[h].x >> 16;
-        code[2] = cc[h].y & 0xFFFFu; code[3] = cc[h].y >> 16; code[4] = 0xFFFFFFFFu;
-        float run[SLAB];
-#pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch) run[ch] = -INFINITY;
-#pragma unroll
-        for (int px = 0; px < 4; ++px) {
-#pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch) run[ch] = fmaxf(run[ch], f[h][ch].v[px]);
-          uint32_t* cell = Pk + (code[px] < CODE_OUTLIER ? code[px] : 0u);
-          if (VEC) {
-            red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
-          } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
-            for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
-          }
-          if (px < 3) {
-            const bool last = code[px + 1] != code[px];
-#pragma unroll
-            for (int ch = 0; ch < SLAB; ++ch) run[ch] = last ? -INFINITY : run[ch];
-          }
-        }
+        nxt[h] = fetch_codes(tn + 2 * NT);
       }
     }
   }

@@ -46,6 +46,12 @@ WSMG_HD int fan_row_width(int y, int E) {
   return w > 0 ? w : 0;
 }
 
+// Cells of the fan before row y (closed form of sum_{t<y} fan_row_width(t, E); rows 0..2 are full width,
+// row t >= 3 has E - 2t + 4 cells).  Valid for y <= E/2 + 1 (the fan's rows).
+WSMG_HD int fan_row_offset(int y, int E) {
+  return y <= 3 ? y * E : 3 * E + (y - 3) * (E + 4) - (y - 1) * y + 6;
+}
+
 // ---------------------------------------------------------------- order-preserving keys
 WSMG_HD uint32_t f2key(float f) {
 #if defined(__CUDA_ARCH__)
