@@ -50,6 +50,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_per_env():
+    """DRAM bytes per env of k_fused from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by scripts/ncu_summary.sh); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))["k_fused_dram_bytes_per_env"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled with NVML while the timed region runs."""
 
@@ -275,6 +285,46 @@ def run_native(args, rank, local_rank, world):
     h2d = ne * 4 * (s["C"] * s["Hf"] * s["Wf"] + s["Hd"] * s["Wd"] + 4)
     d2h = ne * 4 * s["C"] * s["E"] * s["E"]
 
+    # ---- per depth distribution (uniform / near / room), short runs on up to 256 envs ----
+    by_depth = {}
+    if not args.no_by_depth:
+        nd = min(n, 256)
+        gmap_d = torch.zeros(nd, s["G"], s["G"], s["C"], device=dev)
+        dd_ = ops.dims_for((nd,) + tuple(feat.shape[1:]), depth[:nd].shape, nd, s["E"], s["G"], s["resolution"])
+        for kind in DEPTH_KINDS:
+            dk = torch.cat([make_depth(kind, 8, s["Hd"], s["Wd"], cgen)] * (nd // 8 + 1), 0)[:nd].to(dev).contiguous()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+            for k in range(len(ev) + 2):
+                if k >= 2:
+                    ev[k - 2][0].record(stream)
+                rc = lib.wsmg_map_update(P(feat), P(dk), P(gps[k]), P(compass[k]), P(masks[k]), P(gmap_d), P(ego), None,
+                                         P(scratch), scratch.numel(), ctypes.byref(dd_), sp)
+                _lib.check(rc, "wsmg_map_update")
+                if k >= 2:
+                    ev[k - 2][1].record(stream)
+            torch.cuda.synchronize(dev)
+            ms = statistics.median(a.elapsed_time(b) for a, b in ev)
+            _, inv = ops.unproject_index(dk[:8], s["Hf"], s["Wf"], s["E"], s["G"], s["resolution"])
+            by_depth[kind] = {"frames_per_s_per_gpu": nd / (ms / 1e3), "envs": nd,
+                              "writing_pixel_frac": float(1.0 - inv.float().mean())}
+        del gmap_d
+
+    # ---- the reference's PyTorch ops on this GPU (oracle port, device=cuda): the stock comparator ----
+    torch_cuda_fps = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.mapping_oracle import OracleMapper
+        nb = 8
+        orc = OracleMapper(nb, s["C"], device=dev)
+        gp, cp_, mk = gps[:, :nb].contiguous(), compass[:, :nb].contiguous(), masks[:, :nb].contiguous()
+        for k in range(3):
+            orc.step(feat[:nb], depth[:nb], gp[k], cp_[k], mk[k])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(10):
+            orc.step(feat[:nb], depth[:nb], gp[3 + k], cp_[3 + k], mk[3 + k])
+        torch.cuda.synchronize(dev)
+        torch_cuda_fps = nb * 10 / (time.perf_counter() - t0)
+
     # ---- gather (max over ranks) ------------------------------------------------------------
     stats = torch.tensor([elapsed_ms, fused_ms, e2e_ms, checksum], dtype=torch.float64, device=dev)
     if world > 1:
@@ -292,21 +342,27 @@ def run_native(args, rank, local_rank, world):
         B = algorithmic_bytes_per_frame()
         peak, peak_src = measured_peak()
         achieved = B * n / (max_fused / 1e3) / 1e9
+        tr_env = ncu_traffic_per_env()
+        traffic = args.traffic if args.traffic is not None else (tr_env * n if tr_env is not None else None)
         line = {
             "metric": "map-update frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "native", "config": cfg,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic, "kernel": "k_fused", "kernel_ms": max_fused,
+                         "traffic": traffic, "kernel": "k_fused", "kernel_ms": max_fused,
                          "algorithmic_bytes_per_launch": B * n, "peak_source": peak_src,
                          "whole_step_frac": B * n * world / (max_ms / K / 1e3) / 1e9 / (peak * world)},
-            "e2e": {"value": ne * world * Ke / (max_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "envs_per_gpu": ne, "steps": Ke,
+            "e2e": {"value": ne * world * Ke / (max_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "envs_per_gpu": ne, "steps": Ke,
                     "api": "wsmg_map_update_host (pinned host buffers, chunked H2D/compute/D2H)"},
             "gpu_launches": 3 * K * world,
             "clocks": clk.summary(),
             "checksums": [float(x) for x in allst[:, 3]],
+            "by_depth": by_depth,
         }
+        if torch_cuda_fps is not None:
+            line["torch_cuda_baseline"] = {"value": torch_cuda_fps, "unit": "frames/s", "kind": "port",
+                                           "sample": "8 envs/step x 10 steps, the reference's PyTorch ops (oracle port) on the same B200"}
         if world == 1 and not args.no_cpu_baseline:
             fps_cpu, cores, _ = cpu_reference_fps(8, 24, 2)
             line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -329,6 +385,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per k_fused launch from ncu, if known")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-by-depth", action="store_true", help="skip the per-depth-distribution runs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -87,8 +87,8 @@ def unproject_cells(depth_m: torch.Tensor, geo: MapGeometry):
     cx, cy = hd / 2.0, wd / 2.0
     fx = (hd / 2.0) / np.tan(np.deg2rad(90 / 2.0))
     fy = (wd / 2.0) / np.tan(np.deg2rad(90 / 2.0))
-    cols = torch.arange(0, wd).view(1, 1, 1, wd)
-    rows = torch.arange(hd, 0, step=-1).view(1, 1, hd, 1)
+    cols = torch.arange(0, wd, device=d.device).view(1, 1, 1, wd)
+    rows = torch.arange(hd, 0, step=-1, device=d.device).view(1, 1, hd, 1)
     xx = (cols - cx) / fx
     yy = (rows - cy) / fy
     big_x = xx * d
@@ -109,6 +109,7 @@ def subsample_tables(hf: int, wf: int, hd: int):
 def linear_cells(locs: torch.Tensor, ok: torch.Tensor, hf: int, wf: int, geo: MapGeometry):
     """rgb_mapping.py:195-217.  Returns (lin int64 [bs,hf,wf], invalid bool [bs,hf,wf])."""
     ri, ci = subsample_tables(hf, wf, locs.shape[-1])
+    ri, ci = ri.to(locs.device), ci.to(locs.device)
     ss = locs[:, :, ri[:, None], ci].clone()
     bad_in = ~ok[:, :, ri[:, None], ci].squeeze(1)
     e = geo.ego
@@ -123,9 +124,9 @@ def _scatter_max_cells(src: torch.Tensor, lin: torch.Tensor, n_cells: int):
     """torch_scatter.scatter_max semantics (values only): src [bs,C,N], lin [bs,N]."""
     bs, c, n = src.shape
     idx = lin.view(bs, 1, n).expand(bs, c, n)
-    out = torch.full((bs, c, n_cells), torch.finfo(src.dtype).min, dtype=src.dtype)
+    out = torch.full((bs, c, n_cells), torch.finfo(src.dtype).min, dtype=src.dtype, device=src.device)
     out.scatter_reduce_(2, idx, src, reduce="amax", include_self=True)
-    hit = torch.zeros((bs, n_cells), dtype=torch.bool)
+    hit = torch.zeros((bs, n_cells), dtype=torch.bool, device=src.device)
     hit.scatter_(1, lin, torch.ones_like(lin, dtype=torch.bool))
     return torch.where(hit.unsqueeze(1), out, torch.zeros_like(out)), hit
 
@@ -141,11 +142,12 @@ def project_to_ego(feat: torch.Tensor, lin: torch.Tensor, invalid: torch.Tensor,
     proj = proj.view(bs, c, e, e)
     hole = (proj == SENTINEL).float()
     proj = proj * (1 - hole) + hole * (proj - SENTINEL)
-    occ = torch.zeros((bs, e * e), dtype=torch.bool)
+    occ = torch.zeros((bs, e * e), dtype=torch.bool, device=feat.device)
     flat_lin = lin.reshape(bs, -1)
     flat_ok = ~invalid.reshape(bs, -1)
-    for b in range(bs):
-        occ[b, flat_lin[b][flat_ok[b]]] = True
+    cnt = torch.zeros((bs, e * e), dtype=torch.int32, device=feat.device)
+    cnt.scatter_add_(1, flat_lin, flat_ok.to(torch.int32))
+    occ = cnt > 0
     return proj, occ
 
 
@@ -156,7 +158,7 @@ def rotate(x: torch.Tensor, heading: torch.Tensor, trig=None):
         cos_t = torch.cos(heading.squeeze(1))
     else:
         cos_t, sin_t = trig
-    a = torch.zeros(x.size(0), 2, 3)
+    a = torch.zeros(x.size(0), 2, 3, device=x.device)
     a[:, 0, 0] = cos_t
     a[:, 0, 1] = sin_t
     a[:, 1, 0] = -sin_t
@@ -176,10 +178,11 @@ def translation_grid(tx: torch.Tensor, ty: torch.Tensor, size):
 class OracleMapper:
     """Functional restatement of Mapping/RGBMapping (rgb_mapping.py:11-90) on CPU."""
 
-    def __init__(self, num_proc: int, channels: int = 64, geo: MapGeometry = MapGeometry()):
+    def __init__(self, num_proc: int, channels: int = 64, geo: MapGeometry = MapGeometry(), device="cpu"):
         self.geo = geo
         self.channels = channels
-        self.full_global_map = torch.zeros(num_proc, geo.glob, geo.glob, channels)
+        self.device = torch.device(device)      # "cuda": the same torch ops on the GPU (stock-PyTorch comparator of bench.py)
+        self.full_global_map = torch.zeros(num_proc, geo.glob, geo.glob, channels, device=self.device)
         self.last = {}
 
     def stage_cells(self, depth01: torch.Tensor, hf: int, wf: int):
@@ -198,7 +201,7 @@ class OracleMapper:
         lin, invalid = self.stage_cells(depth01, hf, wf)
         proj, occ = project_to_ego(feat, lin, invalid, geo)                  # :266
         rot = rotate(proj, -compass, None if trig is None else trig["neg"])   # :267 / :37
-        canvas = torch.zeros(bs, c, g, g)
+        canvas = torch.zeros(bs, c, g, g, device=feat.device)
         lo, hi = geo.paste_lo, geo.paste_hi
         canvas[:, :, lo:hi, lo:hi] = rot                                     # :40-44
         half = g // 2

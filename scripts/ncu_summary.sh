@@ -31,6 +31,10 @@ with open(f"profiles/{tag}_k_fused_ncu_full.txt", "w") as f:
         rd = float(r[hdr.index('dram__bytes_read.sum')]); wr = float(r[hdr.index('dram__bytes_write.sum')])
         un = units[hdr.index('dram__bytes_read.sum')]
         mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[un]
+        if li == 0:
+            json.dump({"k_fused_dram_bytes_per_env": (rd + wr) * mult / 256, "source": f"profiles/{tag}_k_fused_ncu_full.txt",
+                       "how": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one k_fused launch over 256 envs"},
+                      open("profiles/ncu_traffic.json", "w"))
         f.write(f"dram traffic per launch (read+write)                                           {(rd + wr) * mult:18.0f} byte  (256 envs: {(rd + wr) * mult / 256 / 1e6:.2f} MB/env; algorithmic 20.79 MB/env)\n")
 PY
 ncu -i gpurun_out/prof_fused.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null > /tmp/src_$TAG.csv
