@@ -118,7 +118,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const wsmg_dims* d, cudaStream_t s) {
   const size_t per_env = (size_t)d->G * d->G * d->C;
-  dim3 grid(gmap ? 148 * 2 : 1, d->bs);
+  dim3 grid(gmap ? 16 : 1, d->bs);
   k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags);
   return (int)cudaGetLastError();
 }

@@ -30,6 +30,7 @@ inline Geo make_geo(const wsmg_dims* d) {
   g.cmax = (float)cmax;
   g.cmin = (float)cmin;
   g.cell = (float)((cmax - cmin) / (double)d->G);              // rgb_mapping.py:98 == :146
+  g.inv_cell = 1.0 / (double)g.cell;
   g.half = (float)((d->E - 1) / 2.0);                          // rgb_mapping.py:173
   const double t45 = tan(45.0 * (M_PI / 180.0));               // np.tan(np.deg2rad(fov/2)), fov = 90
   g.cx = (float)(d->Hd / 2.0);                                 // rgb_mapping.py:149

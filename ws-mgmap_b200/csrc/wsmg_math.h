@@ -32,6 +32,7 @@ struct Geo {
   float half;            // (E-1)/2                                rgb_mapping.py:173
   float cx, cy, fx, fy;  // pinhole, 90 deg FoV                    rgb_mapping.py:148-151
   float ksub;            // Wd / Wf                                rgb_mapping.py:189
+  double inv_cell;       // 1.0 / (double)cell, see div_cell()
   float half_e, half_g;  // E/2, G/2 (grid_sampler scaling factor)
   float gcenter;         // G//2                                   rgb_mapping.py:47
 };
@@ -131,12 +132,18 @@ WSMG_HD void gps_cell(const Geo& g, float gps0, float gps1, float* gxc, float* g
 WSMG_HD int sample_index(const Geo& g, int i) { return (int)((float)i * g.ksub); }          // rgb_mapping.py:192-193
 WSMG_HD float pinhole_xx(const Geo& g, int c) { return ((float)c - g.cx) / g.fx; }          // rgb_mapping.py:161
 WSMG_HD float pinhole_yy(const Geo& g, int r) { return ((float)(g.Hd - r) - g.cy) / g.fy; } // rgb_mapping.py:160,162
+// x / cell, correctly rounded, without the IEEE division sequence: the double product x * (1/cell) errs by
+// < 2^-52 relative, while a quotient of two 24-bit floats is never closer than 2^-49 relative to a float
+// rounding boundary unless it is exact -- so rounding the double product to float gives fl(x / cell).
+// (tests: bit-exact cell indices against the oracle's true division, incl. half-cell multiples.)
+WSMG_HD float div_cell(const Geo& g, float x) { return (float)((double)x * g.inv_cell); }
+
 WSMG_HD bool unproject_depth(const Geo& g, float depth01, float xx, float yy, int* x, int* y) {
   float z = depth01 * 10.0f;                                  // rgb_mapping.py:37
   float X = xx * z, Y = yy * z;
   bool ok = (z != 0.0f) && (Y > -1.5f) && (Y < 0.1f);
-  float xf = rintf(X / g.cell + g.half);
-  float yf = rintf(-(z / g.cell) + g.half);
+  float xf = rintf(div_cell(g, X) + g.half);
+  float yf = rintf(-div_cell(g, z) + g.half);
   ok = ok && (xf >= 0.0f) && (xf < (float)g.E) && (yf >= 0.0f) && (yf < (float)g.E);
   *x = ok ? (int)xf : 0;
   *y = ok ? (int)yf : 0;
