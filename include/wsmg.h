@@ -71,6 +71,28 @@ int wsmg_map_update(const float* feat, const float* depth, const float* gps, con
                     const float* mask, float* gmap, float* ego_out, const float* trig,
                     void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream);
 
+/* Optional extras of wsmg_map_update_ex (all fields may be NULL / 0).
+ *   trig        see wsmg_map_update.
+ *   ego_half    [bs,C,E,E] fp16 (IEEE binary16, round-to-nearest-even) copy of ego_out, written by the same
+ *               kernel: what the rollout store keeps (reference common_trainer.py:519-520 casts the fp32 map
+ *               with numpy on the CPU after the forward hook's o.cpu(), dagger_trainer.py:303-306).
+ *   env_slots   [bs] int32: frame b reads / updates map row env_slots[b] (< n_maps) instead of row b, so
+ *               pausing finished envs is an index-table edit instead of the reference's
+ *               full_global_map[state_index] re-materialisation (common_trainer.py:171-172,454-476).
+ *               Slots must be distinct.
+ *   ev_before_fused / ev_after_fused   cudaEvent_t recorded around the k_fused launch (profiling). */
+typedef struct wsmg_opts {
+  const float* trig;
+  void* ego_half;
+  const int32_t* env_slots;
+  void* ev_before_fused;
+  void* ev_after_fused;
+} wsmg_opts;
+
+int wsmg_map_update_ex(const float* feat, const float* depth, const float* gps, const float* compass,
+                       const float* mask, float* gmap, float* ego_out, const wsmg_opts* opts,
+                       void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream);
+
 /* wsmg_map_update, additionally recording two CUDA events (cudaEvent_t passed as void*, either may
  * be NULL) on `stream` immediately before and after the k_fused launch.  bench.py uses it to time the
  * dominant kernel live for the roofline; results are identical to wsmg_map_update. */

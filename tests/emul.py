@@ -40,8 +40,10 @@ def emul_cells(depth, hf, e=100, g=240, res=0.12):
     return lin, inv.astype(bool), codes
 
 
-def emul_step(gmap, feat, depth, gps, compass, masks, trig=None, mode=0, proj_in=None, want_proj=False, e=100, g=240, res=0.12):
-    """gmap [n,G,G,C] updated in place.  trig [bs,4] or None.  Returns (ego, proj or None)."""
+def emul_step(gmap, feat, depth, gps, compass, masks, trig=None, mode=0, proj_in=None, want_proj=False, e=100, g=240, res=0.12,
+              ego_half=None, env_slots=None):
+    """gmap [n,G,G,C] updated in place.  trig [bs,4] or None.  Returns (ego, proj or None).
+    ego_half: optional uint16 array [bs,C,E,E] receiving the fp16 bits; env_slots: optional int32 [bs]."""
     bs, c, hf, wf = feat.shape if feat is not None else (proj_in.shape[0], proj_in.shape[1], 4, 4)
     hd, wd = (depth.shape[1], depth.shape[2]) if depth is not None else (4, 4)
     d = make_dims(bs, gmap.shape[0] if gmap is not None else bs, c, hf, wf, hd, wd, e, g, res)
@@ -51,6 +53,7 @@ def emul_step(gmap, feat, depth, gps, compass, masks, trig=None, mode=0, proj_in
     trig_a = None if trig is None else np.ascontiguousarray(trig, np.float32)
     pin = None if proj_in is None else np.ascontiguousarray(proj_in, np.float32)
     rc = lib().wsmg_emul_step(_p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(gmap), _p(ego),
-                              _p(trig_a), _p(proj), _p(pin), ctypes.c_int(mode), ctypes.byref(d))
+                              _p(trig_a), _p(proj), _p(pin), ctypes.c_int(mode), ctypes.byref(d), _p(ego_half),
+                              _p(None if env_slots is None else np.ascontiguousarray(env_slots, np.int32)))
     assert rc == 0, rc
     return ego, proj

@@ -92,3 +92,36 @@ def test_channel_rebinning_and_input_checks():
     assert _close(out.cpu(), want, 1.0)
     with pytest.raises(ValueError):
         m(feat.to(DEV), dict(depth=depth, gps=obs["gps"], compass=obs["compass"]), torch.zeros(2, 1, device=DEV))  # CPU depth
+
+
+def test_optin_extras_env_slots_and_half_store():
+    """slot table instead of map[state_index]; fp16 ego map for the rollout store."""
+    import numpy as np
+    c, hf, hd, n = 8, 64, 64, 4
+    gen = torch.Generator().manual_seed(3)
+
+    def frame(bs):
+        return (make_features(bs, c, hf, hf, gen), make_depth("room2", bs, hd, hd, gen),
+                torch.randn(bs, 2, generator=gen), torch.rand(bs, 1, generator=gen) * 6 - 3)
+
+    a, b = RGBMapping(_cfg(n, c)), RGBMapping(_cfg(n, c))        # a: reference-style re-indexing, b: slot table
+    b.store_half = True
+    feat, depth, gps, compass = frame(n)
+    obs = lambda: dict(depth=depth.to(DEV), gps=gps.to(DEV), compass=compass.to(DEV))  # noqa: E731
+    oa = a(feat.to(DEV), obs(), torch.zeros(n, 1, device=DEV))
+    ob = b(feat.to(DEV), obs(), torch.zeros(n, 1, device=DEV))
+    assert torch.equal(oa, ob)
+    host = b.ego_half_to_host()
+    torch.cuda.synchronize()
+    assert np.array_equal(host.numpy(), oa.cpu().numpy().astype(np.float16))     # common_trainer.py:519-520
+    keep = [0, 1, 3]
+    a.full_global_map = a.full_global_map[keep]                                  # what _pause_envs does
+    b.pause_envs([2])
+    assert b.env_slots.tolist() == keep and b.full_global_map.shape[0] == n
+    feat, depth, gps, compass = frame(3)
+    oa = a(feat.to(DEV), obs(), torch.ones(3, 1, device=DEV))
+    ob = b(feat.to(DEV), obs(), torch.ones(3, 1, device=DEV))
+    assert torch.equal(oa, ob)
+    assert torch.equal(a.full_global_map, b.full_global_map[keep])
+    b.pause_envs([0])                                                            # slots compose: [1, 3]
+    assert b.env_slots.tolist() == [1, 3]

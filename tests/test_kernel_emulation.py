@@ -135,3 +135,28 @@ def test_device_trig_tolerance_statement():
     eb, _ = emul_step(gb, feat, depth, gps, compass, masks, trig=None)       # libm sinf/cosf
     tol = 1e-5 * np.abs(ea) + 2e-5 * np.abs(feat).max()
     assert (np.abs(ea - eb) <= tol).all()
+
+
+def test_half_output_and_env_slots():
+    """wsmg_opts extras: fp16 copy == numpy astype(float16) of the ego map (what
+    common_trainer.py:519-520 stores); env_slots == the reference's map[state_index] re-indexing."""
+    n, c, hf, hd = 4, 4, 40, 48
+    gen = torch.Generator().manual_seed(5)
+    def frame(bs, signed=False):
+        return (make_features(bs, c, hf, hf, gen, signed=signed).numpy(), make_depth("near", bs, hd, hd, gen)[..., 0].numpy(),
+                torch.randn(bs, 2, generator=gen).numpy(), (torch.rand(bs, 1, generator=gen) * 6 - 3).numpy())
+    g_ref = np.zeros((n, 240, 240, c), np.float32)
+    g_slot = np.zeros((n, 240, 240, c), np.float32)
+    f = frame(n)
+    emul_step(g_ref, *f, np.zeros((n, 1), np.float32))
+    half = np.zeros((n, c, 100, 100), np.uint16)
+    ego, _ = emul_step(g_slot, *f, np.zeros((n, 1), np.float32), ego_half=half, env_slots=np.arange(n))
+    assert np.array_equal(g_ref, g_slot)
+    assert np.array_equal(half.view(np.float16), ego.astype(np.float16))
+    keep = [0, 2, 3]                                   # env 1 finished: reference re-materialises map[keep]
+    g_ref2 = np.ascontiguousarray(g_ref[keep])
+    f = frame(3, signed=True)
+    ego_ref, _ = emul_step(g_ref2, *f, np.ones((3, 1), np.float32))
+    ego_slot, _ = emul_step(g_slot, *f, np.ones((3, 1), np.float32), env_slots=np.array(keep))
+    assert np.array_equal(ego_ref, ego_slot)
+    assert np.array_equal(g_slot[keep], g_ref2) and np.array_equal(g_slot[1], g_ref[1])   # paused env untouched

@@ -17,14 +17,21 @@ class WsmgDims(ctypes.Structure):
     ]
 
 
+class WsmgOpts(ctypes.Structure):
+    _fields_ = [("trig", ctypes.c_void_p), ("ego_half", ctypes.c_void_p), ("env_slots", ctypes.c_void_p),
+                ("ev_before_fused", ctypes.c_void_p), ("ev_after_fused", ctypes.c_void_p)]
+
+
 _P = ctypes.c_void_p
 _DP = ctypes.POINTER(WsmgDims)
+_OP = ctypes.POINTER(WsmgOpts)
 
 SIGNATURES = {
     "wsmg_abi_version": (ctypes.c_int, []),
     "wsmg_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "wsmg_scratch_bytes": (ctypes.c_size_t, [_DP]),
     "wsmg_map_update": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
+    "wsmg_map_update_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _OP, _P, ctypes.c_size_t, _DP, _P]),
     "wsmg_map_update_timed": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P, _P, _P]),
     "wsmg_unproject_index": (ctypes.c_int, [_P, _P, _P, _DP, _P]),
     "wsmg_scatter_max": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),

@@ -23,13 +23,14 @@ constexpr int CELLS_THREADS = 256;
 // ------------------------------------------------------------------ k_reset
 // full_global_map[:bs] *= masks (rgb_mapping.py:35).  mask == 1 (the steady state) touches nothing.
 __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
-                                               size_t per_env, uint32_t* __restrict__ env_flags) {
+                                               size_t per_env, uint32_t* __restrict__ env_flags,
+                                               const int32_t* __restrict__ env_slots) {
   const int b = blockIdx.y;
   if (env_flags != nullptr && blockIdx.x == 0 && threadIdx.x == 0) env_flags[b] = 0u;   // k_cells (next launch) sets them
   if (gmap == nullptr) return;
   const float m = mask[b];
   if (m == 1.0f) return;
-  float* base = gmap + (size_t)b * per_env;
+  float* base = gmap + (size_t)(env_slots != nullptr ? env_slots[b] : b) * per_env;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if ((per_env & 3) == 0) {
@@ -116,10 +117,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 // ------------------------------------------------------------------ host glue
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const wsmg_dims* d, cudaStream_t s) {
+static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const int32_t* env_slots, const wsmg_dims* d,
+                        cudaStream_t s) {
   const size_t per_env = (size_t)d->G * d->G * d->C;
   dim3 grid(gmap ? 16 : 1, d->bs);
-  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags);
+  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags, env_slots);
   return (int)cudaGetLastError();
 }
 
@@ -227,7 +229,8 @@ int wsmg_base_coords_host(float* out_host, int32_t n) {
 
 static int map_update_impl(const float* feat, const float* depth, const float* gps, const float* compass,
                            const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
-                           size_t scratch_bytes_, const wsmg_dims* d, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+                           size_t scratch_bytes_, const wsmg_dims* d, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1,
+                           void* ego_half = nullptr, const int32_t* env_slots = nullptr) {
   int rc = validate_dims(d);
   if (rc != WSMG_OK) return rc;
   if (!feat || !depth || !gps || !compass || !mask || !gmap || !ego_out || !scratch) return WSMG_E_NULL;
@@ -236,13 +239,14 @@ static int map_update_impl(const float* feat, const float* depth, const float* g
   const Geo g = make_geo(d);
   uint16_t* codes = (uint16_t*)scratch;
   uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
-  rc = launch_reset(gmap, mask, flags, d, s);
+  rc = launch_reset(gmap, mask, flags, env_slots, d, s);
   if (rc) return rc;
   rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
   p.feat = feat; p.codes = codes; p.env_flags = flags; p.gps = gps; p.compass = compass; p.trig = trig;
   p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
+  p.ego_half = (uint16_t*)ego_half; p.env_slots = env_slots;
   p.stop_after_scatter = 0; p.bs = d->bs; p.g = g;
   if (ev0) cudaEventRecord(ev0, s);
   rc = launch_fused(p, d->n_maps, s);
@@ -255,6 +259,16 @@ int wsmg_map_update(const float* feat, const float* depth, const float* gps, con
                     size_t scratch_bytes_, const wsmg_dims* d, void* stream) {
   return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, trig, scratch, scratch_bytes_, d,
                          (cudaStream_t)stream, nullptr, nullptr);
+}
+
+int wsmg_map_update_ex(const float* feat, const float* depth, const float* gps, const float* compass,
+                       const float* mask, float* gmap, float* ego_out, const wsmg_opts* o, void* scratch,
+                       size_t scratch_bytes_, const wsmg_dims* d, void* stream) {
+  wsmg_opts z{};
+  if (o == nullptr) o = &z;
+  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, o->trig, scratch, scratch_bytes_, d,
+                         (cudaStream_t)stream, (cudaEvent_t)o->ev_before_fused, (cudaEvent_t)o->ev_after_fused,
+                         o->ego_half, o->env_slots);
 }
 
 int wsmg_map_update_timed(const float* feat, const float* depth, const float* gps, const float* compass,
@@ -283,7 +297,7 @@ int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out, voi
   const Geo g = make_geo(d);
   uint16_t* codes = (uint16_t*)scratch;
   uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
-  rc = launch_reset(nullptr, nullptr, flags, d, s);      // only clears the env flags
+  rc = launch_reset(nullptr, nullptr, flags, nullptr, d, s);      // only clears the env flags
   if (rc) return rc;
   rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
   if (rc) return rc;
@@ -299,7 +313,7 @@ int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const fl
   if (!proj_in || !gps || !compass || !mask || !gmap || !ego_out) return WSMG_E_NULL;
   if (!aligned16(gmap)) return WSMG_E_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
-  rc = launch_reset(gmap, mask, nullptr, d, s);
+  rc = launch_reset(gmap, mask, nullptr, nullptr, d, s);
   if (rc) return rc;
   FusedParams p{};
   p.proj_in = proj_in; p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap; p.ego = ego_out;

@@ -26,6 +26,9 @@
 //   tail  baseE[E], fanrow[E+1], flags
 #pragma once
 #include "wsmg_math.h"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 #if defined(__CUDACC__)
 #define WSMG_BODY __device__ __forceinline__
@@ -122,6 +125,8 @@ struct FusedParams {
   const float* trig;        // optional [bs,4]
   float* gmap;              // [n_maps,G,G,C]
   float* ego;               // [bs,C,E,E]
+  uint16_t* ego_half;       // optional [bs,C,E,E] IEEE binary16 copy of ego (rollout store)
+  const int32_t* env_slots; // optional [bs]: map row of frame b (default b)
   float* proj_out;          // optional dump of the pre-rotation grid [bs,C,E,E]
   const float* proj_in;     // optional: take the grid from here instead of scattering
   int stop_after_scatter;   // stage API: return after writing proj_out
@@ -153,6 +158,7 @@ __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_g
 template <int N> __device__ __forceinline__ void async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ uint16_t f2half_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
 __device__ __forceinline__ unsigned saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // -- mbarrier / TMA (cp.async.bulk.tensor) -------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -206,6 +212,9 @@ inline void async_copy4(void* dst, const void* src, bool pred) {
 }
 inline void async_commit() {}
 template <int N> inline void async_wait() {}
+inline uint16_t f2half_bits(float f) {        // round-to-nearest-even binary16, like numpy's astype(float16)
+  _Float16 h = (_Float16)f; uint16_t u; __builtin_memcpy(&u, &h, 2); return u;
+}
 inline void mbar_init(uint64_t*, int) {}
 inline void mbar_init_fence() {}
 inline void mbar_expect_tx(uint64_t*, unsigned) {}
@@ -277,6 +286,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float qx = 0.f, qy = 0.f;
   int u0 = 0, v0 = 0;
   float* gmap_b = nullptr;
+  const int mrow = p.env_slots != nullptr ? p.env_slots[b] : b;      // row of the caller's map tensor
   if (!p.stop_after_scatter) {
     float gxc, gyc;
     gps_cell(g, p.gps[2 * b], p.gps[2 * b + 1], &gxc, &gyc);
@@ -287,7 +297,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     sx = fminf(fmaxf(sx, -lim), lim);
     u0 = (int)sy + paste_lo - 1;                            // global row / col of window cell (0,0)
     v0 = (int)sx + paste_lo - 1;
-    gmap_b = p.gmap + (size_t)b * G * G * C + c0;
+    gmap_b = p.gmap + (size_t)mrow * G * G * C + c0;
   }
   // TMA stores must not leave the tensor: a window clipped by the map border (agent within ~6 m of the
   // edge of the 28.8 m map) takes the cp.async / st.global path instead.  CTA-uniform.
@@ -307,7 +317,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #endif
         if (tma_lane < rows) {
           const int uu = k * BAND + tma_lane;
-          tma_load_row(ring + 1 + ((uu + S0) % RR) * WWP, &p.tmap, c0, v0, u0 + uu, b, &bars[k]);
+          tma_load_row(ring + 1 + ((uu + S0) % RR) * WWP, &p.tmap, c0, v0, u0 + uu, mrow, &bars[k]);
         }
       }
     } else {
@@ -646,7 +656,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
           const int kb = k - 1;
           if (tma_lane < tma_rows(kb)) {
             const int uu = kb * BAND + tma_lane;
-            tma_store_row(&p.tmap, c0, v0, u0 + uu, b, ring + 1 + ((uu + S0) % RR) * WWP);
+            tma_store_row(&p.tmap, c0, v0, u0 + uu, mrow, ring + 1 + ((uu + S0) % RR) * WWP);
           }
           tma_commit();
         }
@@ -688,6 +698,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #pragma unroll
     for (int ch = 0; ch < SLAB; ++ch)
       if (ch < nch) st_stream(ego_b + (size_t)ch * EE + t, r.v[ch]);
+    if (p.ego_half != nullptr) {
+      uint16_t* half_b = p.ego_half + ((size_t)b * C + c0) * EE;
+#pragma unroll
+      for (int ch = 0; ch < SLAB; ++ch)
+        if (ch < nch) half_b[(size_t)ch * EE + t] = f2half_bits(r.v[ch]);
+    }
   }
   if (TMA && tma_lane >= 0) tma_wait_read<0>();   // the last band's stores must have read their rows before the CTA retires
 }

@@ -51,7 +51,7 @@ int wsmg_emul_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid
 // mode: 0 = whole step, 1 = scatter only (proj_out), 2 = registration only (proj_in)
 int wsmg_emul_step(const float* feat, const float* depth, const float* gps, const float* compass, const float* mask,
                    float* gmap, float* ego_out, const float* trig, float* proj_out, const float* proj_in, int mode,
-                   const wsmg_dims* d) {
+                   const wsmg_dims* d, uint16_t* ego_half, const int32_t* env_slots) {
   int rc = validate_dims(d);
   if (rc) return rc;
   const Geo g = make_geo(d);
@@ -67,13 +67,14 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
     for (int b = 0; b < d->bs; ++b) {
       float m = mask[b];
       if (m == 1.0f) continue;
-      for (size_t i = 0; i < per_env; ++i) gmap[b * per_env + i] = (m == 0.0f) ? 0.0f : gmap[b * per_env + i] * m;
+      float* base = gmap + (size_t)(env_slots ? env_slots[b] : b) * per_env;
+      for (size_t i = 0; i < per_env; ++i) base[i] = (m == 0.0f) ? 0.0f : base[i] * m;
     }
   }
   FusedParams p{};
   p.feat = feat; p.codes = codes.data(); p.env_flags = flags.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
   p.ego = ego_out; p.proj_out = proj_out; p.proj_in = (mode == 2) ? proj_in : nullptr;
-  p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g; p.sp = sp;
+  p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g; p.sp = sp; p.ego_half = ego_half; p.env_slots = env_slots;
   std::vector<unsigned char> smem(sp.total + 128);
   unsigned char* sm = smem.data() + ((128 - ((uintptr_t)smem.data() & 127)) & 127);
   const int slabs = (g.C + SLAB - 1) / SLAB;

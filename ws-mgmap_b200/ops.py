@@ -34,8 +34,11 @@ def alloc_scratch(dims, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
-def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, trig=None, scratch=None, ego=None):
-    """One step.  feat [bs,C,Hf,Wf], depth [bs,Hd,Wd,1], gmap [n,G,G,C] (updated in place).  Returns ego [bs,C,E,E]."""
+def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, trig=None, scratch=None, ego=None,
+               ego_half=None, env_slots=None):
+    """One step.  feat [bs,C,Hf,Wf], depth [bs,Hd,Wd,1], gmap [n,G,G,C] (updated in place).  Returns ego [bs,C,E,E].
+    ego_half: optional fp16 [bs,C,E,E] tensor that receives the rounded copy (rollout store);
+    env_slots: optional int32 [bs] map row per frame (see include/wsmg.h wsmg_opts)."""
     lib = _lib.load()
     dev = gmap.device
     d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution)
@@ -43,10 +46,15 @@ def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, tr
         scratch = alloc_scratch(d, dev)
     if ego is None:
         ego = torch.empty(feat.shape[0], feat.shape[1], e, e, device=dev, dtype=torch.float32)
+    if ego_half is not None and (ego_half.dtype != torch.float16 or tuple(ego_half.shape) != tuple(ego.shape)):
+        raise ValueError("ego_half must be a float16 tensor shaped like the ego map")
+    if env_slots is not None and (env_slots.dtype != torch.int32 or env_slots.numel() != feat.shape[0]):
+        raise ValueError("env_slots must be int32 [bs]")
+    opts = _lib.WsmgOpts(_ptr(trig), _ptr(ego_half), _ptr(env_slots), None, None)
     with torch.cuda.device(dev):
-        rc = lib.wsmg_map_update(_ptr(feat), _ptr(depth), _ptr(gps), _ptr(compass), _ptr(mask), _ptr(gmap), _ptr(ego),
-                                 _ptr(trig), _ptr(scratch), scratch.numel(), ctypes.byref(d), _stream(dev))
-    _lib.check(rc, "wsmg_map_update")
+        rc = lib.wsmg_map_update_ex(_ptr(feat), _ptr(depth), _ptr(gps), _ptr(compass), _ptr(mask), _ptr(gmap), _ptr(ego),
+                                    ctypes.byref(opts), _ptr(scratch), scratch.numel(), ctypes.byref(d), _stream(dev))
+    _lib.check(rc, "wsmg_map_update_ex")
     return ego
 
 

@@ -88,6 +88,10 @@ class Mapping(nn.Module):
         self.full_global_map = torch.zeros(self.num_proc, g, g, c, device=self.device)
         self.agent_view = torch.zeros(self.num_proc, c, g, g, device=self.device)
         self._scratch = None
+        # Opt-in extras beyond the reference's contract; both default to the reference behaviour.
+        self.env_slots = None        # int32 [bs] CUDA tensor: frame b uses map row env_slots[b] (see pause_envs)
+        self.store_half = False      # also emit an fp16 copy of the ego map into self.last_ego_half
+        self.last_ego_half = None
 
     # -- helpers ---------------------------------------------------------------------------
     def _dims(self, bs, n_maps, hf, wf, hd, wd):
@@ -140,9 +144,40 @@ class Mapping(nn.Module):
             raise ValueError("gps must be [bs,2], compass [bs,1], masks [bs,1]")
         dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2])
         scratch = self._scratch_for(dims, dev)
+        slots = self.env_slots
+        if slots is not None and slots.numel() != bs:
+            raise ValueError(f"env_slots has {slots.numel()} entries for a batch of {bs}")
+        half = torch.empty(bs, c, e, e, device=dev, dtype=torch.float16) if self.store_half else None
         ego = ops.map_update(features, depth, gps, compass, masks, full_global_map, e=e, resolution=self.resolution,
-                             trig=_trig, scratch=scratch)
+                             trig=_trig, scratch=scratch, ego_half=half, env_slots=slots)
+        self.last_ego_half = half
         return ego, full_global_map
+
+    # -- opt-in extras ---------------------------------------------------------------------
+    def pause_envs(self, envs_to_pause):
+        """O(1) replacement for the trainers' `full_global_map = full_global_map[state_index]`
+        (common_trainer.py:171-172,454-476): instead of re-materialising the map tensor, drop the paused
+        envs from the slot table; the map tensor keeps its rows.  Batch element b then updates row
+        env_slots[b].  Callers that use this must NOT also re-index full_global_map."""
+        n = self.full_global_map.shape[0]
+        slots = list(range(n)) if self.env_slots is None else self.env_slots.tolist()
+        for idx in sorted(envs_to_pause, reverse=True):
+            slots.pop(idx)
+        self.env_slots = torch.tensor(slots, dtype=torch.int32, device=self.full_global_map.device)
+        return self.env_slots
+
+    def reset_slots(self):
+        self.env_slots = None
+
+    def ego_half_to_host(self, pinned_out=None, non_blocking=True):
+        """Asynchronous D2H of the fp16 ego map written by the last update (store_half=True): half the bytes of
+        the forward hook's `o.cpu()` (dagger_trainer.py:303-306) and no CPU-side astype (common_trainer.py:519-520)."""
+        if self.last_ego_half is None:
+            raise RuntimeError("store_half is off or no update has run yet")
+        if pinned_out is None:
+            pinned_out = torch.empty(self.last_ego_half.shape, dtype=torch.float16, pin_memory=True)
+        pinned_out.copy_(self.last_ego_half, non_blocking=non_blocking)
+        return pinned_out
 
 
 class RGBMapping(Mapping):
