@@ -137,7 +137,7 @@ struct FusedParams {
 
 // ------------------------------------------------------------------ platform shims
 #if defined(__CUDACC__)
-__device__ __forceinline__ void smem_max(uint32_t* a, uint32_t v) { atomicMax(a, v); }
+__device__ __forceinline__ void smem_max(int32_t* a, int32_t v) { atomicMax(a, v); }
 __device__ __forceinline__ F4 ld_stream4(const float* p) {
   float4 t = __ldcs(reinterpret_cast<const float4*>(p));
   F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
@@ -190,17 +190,17 @@ template <int N> __device__ __forceinline__ void tma_wait_read() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // four predicated shared-memory max-reductions (one per channel plane), predicate evaluated in PTX:
 // the pixel writes (code < 0xFFFE) and closes its run (code != next).  No branch, no predicate spill.
-__device__ __forceinline__ void red_max4(uint32_t* cell, int npp, unsigned code, unsigned next,
-                                         uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+__device__ __forceinline__ void red_max4(int32_t* cell, int npp, unsigned code, unsigned next,
+                                         int32_t k0, int32_t k1, int32_t k2, int32_t k3) {
   unsigned a = saddr(cell);
   asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %4, %5;\n setp.lt.and.u32 p, %4, 0xFFFE, p;\n"
-               " @p red.shared.max.u32 [%0], %6;\n @p red.shared.max.u32 [%1], %7;\n"
-               " @p red.shared.max.u32 [%2], %8;\n @p red.shared.max.u32 [%3], %9;\n}\n"
+               " @p red.shared.max.s32 [%0], %6;\n @p red.shared.max.s32 [%1], %7;\n"
+               " @p red.shared.max.s32 [%2], %8;\n @p red.shared.max.s32 [%3], %9;\n}\n"
                ::"r"(a), "r"(a + 4 * npp), "r"(a + 8 * npp), "r"(a + 12 * npp), "r"(code), "r"(next),
                  "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
 }
 #else
-inline void smem_max(uint32_t* a, uint32_t v) { if (v > *a) *a = v; }
+inline void smem_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
 inline F4 ld_stream4(const float* p) { F4 r; for (int i = 0; i < 4; ++i) r.v[i] = p[i]; return r; }
 inline uint2 ld_codes(const uint2* p) { return *p; }
 inline void st_stream(float* p, float v) { *p = v; }
@@ -224,7 +224,7 @@ inline void tma_store_row(const void*, int, int, int, int, const void*) {}
 inline void tma_commit() {}
 template <int N> inline void tma_wait_read() {}
 inline void fence_proxy_async() {}
-inline void red_max4(uint32_t* cell, int npp, unsigned code, unsigned next, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
+inline void red_max4(int32_t* cell, int npp, unsigned code, unsigned next, int32_t k0, int32_t k1, int32_t k2, int32_t k3) {
   if (code < 0xFFFEu && code != next) {
     smem_max(cell, k0); smem_max(cell + npp, k1); smem_max(cell + 2 * npp, k2); smem_max(cell + 3 * npp, k3);
   }
@@ -269,7 +269,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   const int NB = (WW + BAND - 1) / BAND;
 
   F4* X = reinterpret_cast<F4*>(smem + sp.x_off);            // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
-  uint32_t* Pk = reinterpret_cast<uint32_t*>(smem + sp.r2_off);
+  int32_t* Pk = reinterpret_cast<int32_t*>(smem + sp.r2_off);
   F4* Pf = reinterpret_cast<F4*>(smem + sp.z_off);           // Pf[0] = zero cell, fan cell c at Pf[1 + c]
   F4* ring = reinterpret_cast<F4*>(smem + sp.z_off);         // ring[0] = zero cell, (slot, col) at ring[1 + slot*WWP + col]
   I4* colT = reinterpret_cast<I4*>(smem + sp.tab_off);
@@ -364,7 +364,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   }
   if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); }
   for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
-  for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = 0u;
+  for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = KEY_EMPTY;
   WSMG_SYNC();
 
   // ---- phase 1: scatter-max into the packed fan (rgb_mapping.py:210-225) -----------------------
@@ -401,30 +401,35 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       for (int h = 0; h < 2; ++h) {
         const int tt = t + h * NT;
         if (live[h]) {
-          // Runs of equal codes are reduced in registers (float max; the sign of a zero is irrelevant,
-          // finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
-          // channel.  A pixel that does not write never flushes and is always followed by a reset before
-          // the next flush, so its value needs no masking.
+          // Runs of equal codes are reduced in registers with a predicated running max (the sign of a zero is
+          // irrelevant, finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
+          // channel.  A pixel that does not write never flushes, and the run restarts whenever the code changes,
+          // so its value needs no masking.  When all 16 values are non-negative (post-ReLU features) their bit
+          // patterns already are the keys.
           unsigned code[5];
           code[0] = cc[h].x & 0xFFFFu; code[1] = cc[h].x >> 16;
           code[2] = cc[h].y & 0xFFFFu; code[3] = cc[h].y >> 16; code[4] = 0xFFFFFFFFu;
+          int32_t sign = 0;
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch)
+            if (ch < nch) sign |= f_bits(f[h][ch].v[0]) | f_bits(f[h][ch].v[1]) | f_bits(f[h][ch].v[2]) | f_bits(f[h][ch].v[3]);
+          const bool nonneg = sign >= 0;
           float run[SLAB];
 #pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch) run[ch] = -INFINITY;
-#pragma unroll
           for (int px = 0; px < 4; ++px) {
+            const bool same = px > 0 && code[px] == code[px - 1];
 #pragma unroll
-            for (int ch = 0; ch < SLAB; ++ch) run[ch] = fmaxf(run[ch], f[h][ch].v[px]);
-            uint32_t* cell = Pk + (code[px] < CODE_OUTLIER ? code[px] : 0u);
+            for (int ch = 0; ch < SLAB; ++ch) {
+              float m = f[h][ch].v[px];
+              if (same) m = fmaxf(run[ch], m);
+              run[ch] = m;
+            }
+            int32_t* cell = Pk + code[px];                   // (only dereferenced under the write predicate)
             if (VEC) {
-              red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
+              if (nonneg) red_max4(cell, npp, code[px], code[px + 1], f_bits(run[0]), f_bits(run[1]), f_bits(run[2]), f_bits(run[3]));
+              else red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
             } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
               for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
-            }
-            if (px < 3) {
-              const bool last = code[px + 1] != code[px];
-#pragma unroll
-              for (int ch = 0; ch < SLAB; ++ch) run[ch] = last ? -INFINITY : run[ch];
             }
           }
         }
@@ -444,13 +449,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 
   // ---- phase 1b: keys -> finished floats, planar -> F4 per cell (rgb_mapping.py:228-230) -----
   if (p.proj_in == nullptr) {
-    const uint32_t sentinel_key = f2key(SENTINEL);
+    const int32_t sentinel_key = f2key(SENTINEL);
     const bool inv = (p.env_flags[b] & 1u) != 0;
     for (int t = tid; t < fan_cells; t += NT) {
       F4 v;
 #pragma unroll
       for (int ch = 0; ch < SLAB; ++ch) {
-        uint32_t k = Pk[ch * npp + t];
+        int32_t k = Pk[ch * npp + t];
         if (t == 0 && inv && k < sentinel_key) k = sentinel_key;   // invalid pixels write -1e16 to cell 0 (:207-212)
         v.v[ch] = ch < nch ? finish_cell(k) : 0.0f;
       }

@@ -54,26 +54,30 @@ WSMG_HD int fan_row_offset(int y, int E) {
 }
 
 // ---------------------------------------------------------------- order-preserving keys
-WSMG_HD uint32_t f2key(float f) {
+// Signed 32-bit keys whose integer order is the float order: a non-negative float is its own bit pattern
+// (no work for post-ReLU features), a negative one flips its magnitude bits.  INT32_MIN is produced by no
+// float (-NaN aside) and marks "no valid pixel".
+constexpr int32_t KEY_EMPTY = (int32_t)0x80000000;
+WSMG_HD int32_t f_bits(float f) {
 #if defined(__CUDA_ARCH__)
-  uint32_t b = __float_as_uint(f);
+  return __float_as_int(f);
 #else
-  uint32_t b; __builtin_memcpy(&b, &f, 4);
+  int32_t b; __builtin_memcpy(&b, &f, 4); return b;
 #endif
-  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // negative: ~b, else b | sign
 }
-WSMG_HD float key2f(uint32_t k) {
-  uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+WSMG_HD int32_t f2key(float f) { int32_t b = f_bits(f); return b ^ ((b >> 31) & 0x7FFFFFFF); }
+WSMG_HD float key2f(int32_t k) {
+  int32_t b = k ^ ((k >> 31) & 0x7FFFFFFF);
 #if defined(__CUDA_ARCH__)
-  return __uint_as_float(b);
+  return __int_as_float(b);
 #else
   float f; __builtin_memcpy(&f, &b, 4); return f;
 #endif
 }
-// key 0 = "no valid pixel".  Final value per rgb_mapping.py:220-230: empty -> 0,
-// == -1e16 -> 0, otherwise x + 0*(x+1e16) which only turns -0.0 into +0.0.
-WSMG_HD float finish_cell(uint32_t k) {
-  if (k == 0u) return 0.0f;
+// Final value per rgb_mapping.py:220-230: empty -> 0, == -1e16 -> 0, otherwise x + 0*(x+1e16) which only
+// turns -0.0 into +0.0.
+WSMG_HD float finish_cell(int32_t k) {
+  if (k == KEY_EMPTY) return 0.0f;
   float v = key2f(k);
   return (v == SENTINEL) ? 0.0f : v + 0.0f;
 }
