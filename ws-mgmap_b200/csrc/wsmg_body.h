@@ -372,78 +372,84 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
     const float* plane0 = p.feat + ((size_t)b * C + c0) * HW;
     const int n4 = HW / 4;
-    // Two slots (4-pixel groups tid + h*NT, stepping by 2*NT) rotate: as soon as a slot has been scattered its
-    // next group's feature loads are issued, so one group is always in flight while the other is reduced.
-    // Codes run one more step ahead (nxt), so their L2 latency never sits in front of the feature loads.
+    // Feature staging through shared memory: X is idle until phase 2, so every thread owns STAGES private
+    // 64-byte slots in it ([slot][channel][thread] float4s: conflict-free) and keeps STAGES groups (4 pixels x 4
+    // channels) in flight with cp.async while it reduces the oldest one -- no registers are tied up by loads in
+    // flight and no barrier is involved (a thread only ever reads what it copied itself).
+    // Codes run STAGES steps ahead of the features, so their L2 latency never sits in front of a feature copy.
     // Valid pixels carry a fan cell (< CODE_OUTLIER): every u16 lane of (x & y) has its top 15 bits set iff none of
     // the four pixels writes -- such a group skips its feature read.
-    uint2 cc[2], nxt[2];
-    bool live[2];
-    F4 f[2][SLAB];
+    constexpr int STAGES = 2;
+    F4* stage = X + 1;                                        // [STAGES][SLAB][NT]
+    uint2 cq[STAGES + 1];                                     // codes of the groups in flight (+1: next to be issued)
     auto fetch_codes = [&](int tt) -> uint2 {
       uint2 c; c.x = c.y = 0xFFFFFFFFu;
       if (tt < n4) c = ld_codes(codes4 + tt);
       return c;
     };
-#pragma unroll
-    for (int h = 0; h < 2; ++h) cc[h] = fetch_codes(tid + h * NT);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      nxt[h] = fetch_codes(tid + (2 + h) * NT);
-      live[h] = ((cc[h].x & cc[h].y) | 0x00010001u) != 0xFFFFFFFFu;
-      const float* src = plane0 + 4 * (size_t)(tid + h * NT);
-#pragma unroll
-      for (int ch = 0; ch < SLAB; ++ch)
-        if (live[h] && ch < nch) f[h][ch] = ld_stream4(src + (size_t)ch * HW);
-    }
-    for (int t = tid; t < n4; t += 2 * NT) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int tt = t + h * NT;
-        if (live[h]) {
-          // Runs of equal codes are reduced in registers with a predicated running max (the sign of a zero is
-          // irrelevant, finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
-          // channel.  A pixel that does not write never flushes, and the run restarts whenever the code changes,
-          // so its value needs no masking.  When all 16 values are non-negative (post-ReLU features) their bit
-          // patterns already are the keys.
-          unsigned code[5];
-          code[0] = cc[h].x & 0xFFFFu; code[1] = cc[h].x >> 16;
-          code[2] = cc[h].y & 0xFFFFu; code[3] = cc[h].y >> 16; code[4] = 0xFFFFFFFFu;
-          int32_t sign = 0;
-#pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch)
-            if (ch < nch) sign |= f_bits(f[h][ch].v[0]) | f_bits(f[h][ch].v[1]) | f_bits(f[h][ch].v[2]) | f_bits(f[h][ch].v[3]);
-          const bool nonneg = sign >= 0;
-          float run[SLAB];
-#pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            const bool same = px > 0 && code[px] == code[px - 1];
-#pragma unroll
-            for (int ch = 0; ch < SLAB; ++ch) {
-              float m = f[h][ch].v[px];
-              if (same) m = fmaxf(run[ch], m);
-              run[ch] = m;
-            }
-            int32_t* cell = Pk + code[px];                   // (only dereferenced under the write predicate)
-            if (VEC) {
-              if (nonneg) red_max4(cell, npp, code[px], code[px + 1], f_bits(run[0]), f_bits(run[1]), f_bits(run[2]), f_bits(run[3]));
-              else red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
-            } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
-              for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
-            }
-          }
-        }
-        // refill this slot with group tt + 2*NT
-        const int tn = tt + 2 * NT;
-        cc[h] = nxt[h];
-        live[h] = ((cc[h].x & cc[h].y) | 0x00010001u) != 0xFFFFFFFFu;      // (codes past the end are 0xFFFF)
-        const float* src = plane0 + 4 * (size_t)tn;
+    auto is_live = [](uint2 c) { return ((c.x & c.y) | 0x00010001u) != 0xFFFFFFFFu; };   // (codes past the end are 0xFFFF)
+    auto issue = [&](int slot, int tt, uint2 c) {
+      if (is_live(c)) {
+        const float* src = plane0 + 4 * (size_t)tt;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
-          if (live[h] && ch < nch) f[h][ch] = ld_stream4(src + (size_t)ch * HW);
-        nxt[h] = fetch_codes(tn + 2 * NT);
+          if (ch < nch) async_copy16(stage + (slot * SLAB + ch) * NT + tid, src + (size_t)ch * HW, true);
       }
+      async_commit();                                          // one group per step, live or not: wait counts stay exact
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < STAGES; ++s_) {
+      cq[s_] = fetch_codes(tid + s_ * NT);
+      issue(s_, tid + s_ * NT, cq[s_]);
     }
+    cq[STAGES] = fetch_codes(tid + STAGES * NT);
+    for (int t = tid, it = 0; t < n4; t += NT, ++it) {
+      const int slot = it % STAGES;
+      const uint2 cc = cq[0];
+      async_wait<STAGES - 1>();                                // this group's copies have landed
+      if (is_live(cc)) {
+        F4 f[SLAB];
+#pragma unroll
+        for (int ch = 0; ch < SLAB; ++ch) f[ch] = ch < nch ? stage[(slot * SLAB + ch) * NT + tid] : f4_zero();
+        // Runs of equal codes are reduced in registers with a predicated running max (the sign of a zero is
+        // irrelevant, finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
+        // channel.  A pixel that does not write never flushes, and the run restarts whenever the code changes,
+        // so its value needs no masking.  When all 16 values are non-negative (post-ReLU features) their bit
+        // patterns already are the keys.
+        unsigned code[5];
+        code[0] = cc.x & 0xFFFFu; code[1] = cc.x >> 16;
+        code[2] = cc.y & 0xFFFFu; code[3] = cc.y >> 16; code[4] = 0xFFFFFFFFu;
+        int32_t sign = 0;
+#pragma unroll
+        for (int ch = 0; ch < SLAB; ++ch)
+          if (ch < nch) sign |= f_bits(f[ch].v[0]) | f_bits(f[ch].v[1]) | f_bits(f[ch].v[2]) | f_bits(f[ch].v[3]);
+        const bool nonneg = sign >= 0;
+        float run[SLAB];
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const bool same = px > 0 && code[px] == code[px - 1];
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch) {
+            float m = f[ch].v[px];
+            if (same) m = fmaxf(run[ch], m);
+            run[ch] = m;
+          }
+          int32_t* cell = Pk + code[px];                     // (only dereferenced under the write predicate)
+          if (VEC) {
+            if (nonneg) red_max4(cell, npp, code[px], code[px + 1], f_bits(run[0]), f_bits(run[1]), f_bits(run[2]), f_bits(run[3]));
+            else red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
+          } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
+            for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
+          }
+        }
+      }
+      // refill the slot just consumed with the group STAGES steps ahead; advance the code queue
+#pragma unroll
+      for (int s_ = 0; s_ < STAGES; ++s_) cq[s_] = cq[s_ + 1];
+      issue(slot, t + STAGES * NT, cq[STAGES - 1]);
+      cq[STAGES] = fetch_codes(t + (STAGES + 1) * NT);
+    }
+    async_wait<0>();
   }
   WSMG_SYNC();
 
