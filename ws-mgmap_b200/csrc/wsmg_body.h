@@ -434,12 +434,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
             if (same) m = fmaxf(run[ch], m);
             run[ch] = m;
           }
-          int32_t* cell = Pk + code[px];                     // (only dereferenced under the write predicate)
-          if (VEC) {
-            if (nonneg) red_max4(cell, npp, code[px], code[px + 1], f_bits(run[0]), f_bits(run[1]), f_bits(run[2]), f_bits(run[3]));
-            else red_max4(cell, npp, code[px], code[px + 1], f2key(run[0]), f2key(run[1]), f2key(run[2]), f2key(run[3]));
-          } else if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
-            for (int ch = 0; ch < nch; ++ch) smem_max(cell + ch * npp, f2key(run[ch]));
+          // ptxas turns a predicated shared atomic into its own branch region, so one branch per pixel (the
+          // predicate is shared by the four channel planes) is the cheapest form
+          if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
+            int32_t* cell = Pk + code[px];
+#pragma unroll
+            for (int ch = 0; ch < SLAB; ++ch)
+              if (ch < nch) smem_max(cell + ch * npp, nonneg ? f_bits(run[ch]) : f2key(run[ch]));
           }
         }
       }
@@ -519,9 +520,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
       Tap1D tx = make_tap(ix), ty = make_tap(iy);
       int y0 = ty.i0, y1 = ty.i0 + 1;
-      I2 r0 = fanrow[(unsigned)y0 < (unsigned)E ? y0 : E];
-      I2 r1 = fanrow[(unsigned)y1 < (unsigned)E ? y1 : E];
-      const int ia = fan_idx(r0, tx.i0), ib = fan_idx(r0, tx.i0 + 1), ic = fan_idx(r1, tx.i0), id = fan_idx(r1, tx.i0 + 1);
+      int ia = 0, ib = 0, ic = 0, id = 0;
+      if (y1 >= 0 && y0 < g.fan_rows) {                      // half of the grid samples rows the fan does not have
+        I2 r0 = fanrow[(unsigned)y0 < (unsigned)E ? y0 : E];
+        I2 r1 = fanrow[(unsigned)y1 < (unsigned)E ? y1 : E];
+        ia = fan_idx(r0, tx.i0); ib = fan_idx(r0, tx.i0 + 1); ic = fan_idx(r1, tx.i0); id = fan_idx(r1, tx.i0 + 1);
+      }
       hit = (ia | ib | ic | id) != 0;
       if (hit) {
         Weights w = make_weights(tx.w1, ty.w1);
