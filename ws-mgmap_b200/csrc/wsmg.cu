@@ -53,19 +53,40 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
 
 // ------------------------------------------------------------------ k_cells
 // Fused unproject + height-band test + bin + index.  Each thread owns four consecutive sampled pixels
-// of the Hf x Wf frame (one 8-byte store of packed fan codes); the per-column pinhole term and source
-// column live in shared-memory tables built once per block, the per-row term is one division per
-// thread.  Also emits the reference-shaped (linear index, invalid) pair for the stage API and the
-// per-env "some pixel does not write" flag (those pixels send the sentinel to cell 0,
-// rgb_mapping.py:207-212).
+// of the Hf x Wf frame (one 8-byte store of packed fan codes).  The depth rows a block needs are one
+// contiguous span of the depth image: a single TMA bulk copy (cp.async.bulk + mbarrier complete_tx)
+// stages them in shared memory while the per-column pinhole table is being built; the nearest-
+// neighbour subsampling (rgb_mapping.py:188-196) then gathers from shared memory.  Also emits the
+// reference-shaped (linear index, invalid) pair for the stage API and the per-env "some pixel does not
+// write" flag (those pixels send the sentinel to cell 0, rgb_mapping.py:207-212).
 constexpr int CELLS_PX = 4;
 constexpr int CELLS_MAX_W = 1024;
 __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
                                                           int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
-                                                          uint32_t* __restrict__ env_flags, Geo g) {
+                                                          uint32_t* __restrict__ env_flags, Geo g, int stage_rows) {
+  extern __shared__ __align__(128) unsigned char cells_smem[];
   __shared__ int rowoff[160];
   __shared__ int col_src[CELLS_MAX_W];
   __shared__ float col_xx[CELLS_MAX_W];
+  __shared__ __align__(8) uint64_t bar;
+  float* drows = reinterpret_cast<float*>(cells_smem);       // [stage_rows][Wd] when stage_rows > 0
+  const int b = blockIdx.y;
+  const int HW = g.Hf * g.Wf;
+  const int per_block = CELLS_THREADS * CELLS_PX;
+  const int t_first = blockIdx.x * per_block;
+  const int t_last = (t_first + per_block < HW ? t_first + per_block : HW) - 1;
+  const float* depth_b = depth + (size_t)b * g.Hd * g.Wd;
+  const int r_first = sample_index(g, t_first / g.Wf);
+  const int n_rows = sample_index(g, t_last / g.Wf) - r_first + 1;
+  const bool staged = stage_rows > 0 && n_rows <= stage_rows;
+  if (staged && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_init_fence();
+    const unsigned bytes = (unsigned)(n_rows * g.Wd * 4);
+    mbar_expect_tx(&bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(saddr(drows)), "l"(depth_b + (size_t)r_first * g.Wd), "r"(bytes), "r"(saddr(&bar)) : "memory");
+  }
   for (int t = threadIdx.x; t < g.fan_rows; t += blockDim.x) rowoff[t] = fan_row_offset(t, g.E);
   for (int j = threadIdx.x; j < g.Wf; j += blockDim.x) {
     int c = sample_index(g, j);
@@ -73,10 +94,8 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
     col_xx[j] = pinhole_xx(g, c);
   }
   __syncthreads();
-  const int b = blockIdx.y;
-  const int HW = g.Hf * g.Wf;
-  const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * CELLS_PX;
-  const float* depth_b = depth + (size_t)b * g.Hd * g.Wd;
+  if (staged) mbar_wait(&bar, 0);
+  const int t0 = t_first + threadIdx.x * CELLS_PX;
   int i = t0 / g.Wf, j = t0 - i * g.Wf;
   int r = sample_index(g, i);
   float yy = pinhole_yy(g, r);
@@ -88,7 +107,8 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
     code[px] = CODE_INVALID;
     if (t < HW) {
       int x, y;
-      const bool ok = unproject_depth(g, depth_b[(size_t)r * g.Wd + col_src[j]], col_xx[j], yy, &x, &y);
+      const float dval = staged ? drows[(r - r_first) * g.Wd + col_src[j]] : depth_b[(size_t)r * g.Wd + col_src[j]];
+      const bool ok = unproject_depth(g, dval, col_xx[j], yy, &x, &y);
       any_bad |= !ok;
       if (ok) {
         if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
@@ -131,7 +151,12 @@ static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8
   const int HW = g.Hf * g.Wf;
   const int per_block = CELLS_THREADS * CELLS_PX;
   dim3 grid((HW + per_block - 1) / per_block, bs);
-  k_cells<<<grid, CELLS_THREADS, 0, s>>>(depth, codes, lin, invalid, env_flags, g);
+  // depth rows one block can touch: its sampled rows (per_block / Wf + 2) times the subsampling ratio, + 1
+  int stage_rows = (int)((per_block / g.Wf + 2) * (double)g.Hd / g.Hf) + 2;
+  size_t smem = (size_t)stage_rows * g.Wd * 4;
+  const bool bulk_ok = (g.Wd % 4) == 0 && (((size_t)g.Hd * g.Wd) % 4) == 0 && (reinterpret_cast<uintptr_t>(depth) & 15u) == 0;
+  if (smem > 32 * 1024 || !bulk_ok) { stage_rows = 0; smem = 0; }     // fall back to direct global gathers
+  k_cells<<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, g, stage_rows);
   return (int)cudaGetLastError();
 }
 
