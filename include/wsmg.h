@@ -57,6 +57,16 @@ const char* wsmg_error_string(int code);
 /* Bytes of device scratch wsmg_map_update needs for `d` (packed cell codes + flags). */
 size_t wsmg_scratch_bytes(const wsmg_dims* d);
 
+/* Per-env status words the update leaves in scratch (uint32 each, at byte offset wsmg_scratch_flags_offset(d)):
+ *   WSMG_FLAG_INVALID_PIXEL  some pixel of the frame does not write (normal: sky, holes, out of range)
+ *   WSMG_FLAG_OUTSIDE_FAN    a *valid* pixel fell outside the packed fan the scatter keeps in shared memory.
+ *                            Only depth < 0 can do that (Habitat depth is in [0,1]); such pixels are DROPPED,
+ *                            which the reference would not do -- callers that cannot rule them out should check
+ *                            this bit (the Python module raises when `strict_inputs` is set). */
+#define WSMG_FLAG_INVALID_PIXEL 1u
+#define WSMG_FLAG_OUTSIDE_FAN 2u
+size_t wsmg_scratch_flags_offset(const wsmg_dims* d);
+
 /* Whole step: Mapping.project_feat_to_map (rgb_mapping.py:32-72) as called by
  * RGBMapping.forward (rgb_mapping.py:85).
  *   feat     [bs,C,Hf,Wf] fp32 NCHW          (rgb_features after the identity channel pool, :81-84)

@@ -125,3 +125,17 @@ def test_optin_extras_env_slots_and_half_store():
     assert torch.equal(a.full_global_map, b.full_global_map[keep])
     b.pause_envs([0])                                                            # slots compose: [1, 3]
     assert b.env_slots.tolist() == [1, 3]
+
+
+def test_strict_inputs_flags_negative_depth():
+    m = RGBMapping(_cfg(2, 4))
+    m.strict_inputs = True
+    gen = torch.Generator().manual_seed(4)
+    feat = make_features(2, 4, 32, 32, gen)
+    depth = make_depth("near", 2, 32, 32, gen)
+    obs = dict(depth=depth.to(DEV), gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
+    m(feat.to(DEV), obs, torch.zeros(2, 1, device=DEV))                     # fine
+    depth[1, 20:, :, 0] = -0.2                                              # behind the camera: not representable
+    obs = dict(depth=depth.to(DEV), gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
+    with pytest.raises(ValueError, match="envs \\[1\\]"):
+        m(feat.to(DEV), obs, torch.ones(2, 1, device=DEV))

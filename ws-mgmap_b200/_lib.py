@@ -30,6 +30,7 @@ SIGNATURES = {
     "wsmg_abi_version": (ctypes.c_int, []),
     "wsmg_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "wsmg_scratch_bytes": (ctypes.c_size_t, [_DP]),
+    "wsmg_scratch_flags_offset": (ctypes.c_size_t, [_DP]),
     "wsmg_map_update": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
     "wsmg_map_update_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _OP, _P, ctypes.c_size_t, _DP, _P]),
     "wsmg_map_update_timed": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P, _P, _P]),
@@ -40,6 +41,9 @@ SIGNATURES = {
     "wsmg_host_staging_bytes": (ctypes.c_size_t, [_DP, ctypes.c_int32]),
     "wsmg_map_update_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP, _P]),
 }
+
+FLAG_INVALID_PIXEL = 1
+FLAG_OUTSIDE_FAN = 2
 
 _lib = None
 

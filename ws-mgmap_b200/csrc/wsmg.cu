@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   int r = sample_index(g, i);
   float yy = pinhole_yy(g, r);
   uint32_t code[CELLS_PX];
-  bool any_bad = false;
+  bool any_bad = false, any_outlier = false;
 #pragma unroll
   for (int px = 0; px < CELLS_PX; ++px) {
     const int t = t0 + px;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
       any_bad |= !ok;
       if (ok) {
         if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
-        else code[px] = CODE_OUTLIER;
+        else { code[px] = CODE_OUTLIER; any_outlier = true; }
       }
       if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
       if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
     *reinterpret_cast<uint2*>(codes + (size_t)b * HW + t0) = w;
   }
   const unsigned bad = __ballot_sync(0xFFFFFFFFu, any_bad);
-  if (env_flags != nullptr && bad != 0u && (threadIdx.x & 31) == 0) atomicOr(env_flags + b, 1u);
+  const unsigned outl = __ballot_sync(0xFFFFFFFFu, any_outlier);
+  if (env_flags != nullptr && (bad | outl) != 0u && (threadIdx.x & 31) == 0)
+    atomicOr(env_flags + b, (bad ? WSMG_FLAG_INVALID_PIXEL : 0u) | (outl ? WSMG_FLAG_OUTSIDE_FAN : 0u));
 }
 
 // ------------------------------------------------------------------ k_fused
@@ -243,6 +245,11 @@ const char* wsmg_error_string(int code) {
 size_t wsmg_scratch_bytes(const wsmg_dims* d) {
   if (validate_dims(d) != WSMG_OK) return 0;
   return scratch_bytes(d);
+}
+
+size_t wsmg_scratch_flags_offset(const wsmg_dims* d) {
+  if (validate_dims(d) != WSMG_OK) return 0;
+  return scratch_codes_bytes(d);
 }
 
 int wsmg_base_coords_host(float* out_host, int32_t n) {

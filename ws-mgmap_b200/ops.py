@@ -58,6 +58,13 @@ def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, tr
     return ego
 
 
+def env_flags(scratch, dims):
+    """Per-env status words of the last update that used `scratch` (synchronises): int32 [bs], bits
+    _lib.FLAG_INVALID_PIXEL / _lib.FLAG_OUTSIDE_FAN (see include/wsmg.h)."""
+    off = int(_lib.load().wsmg_scratch_flags_offset(ctypes.byref(dims)))
+    return scratch[off:off + 4 * dims.bs].view(torch.int32).cpu()
+
+
 def unproject_index(depth, hf, wf, e=100, g=240, resolution=0.12):
     """depth [bs,Hd,Wd,1] -> (lin int32 [bs,hf,wf], invalid bool [bs,hf,wf])."""
     lib = _lib.load()

@@ -92,6 +92,7 @@ class Mapping(nn.Module):
         self.env_slots = None        # int32 [bs] CUDA tensor: frame b uses map row env_slots[b] (see pause_envs)
         self.store_half = False      # also emit an fp16 copy of the ego map into self.last_ego_half
         self.last_ego_half = None
+        self.strict_inputs = False   # debugging aid: synchronise after each update and raise if a valid pixel was dropped
 
     # -- helpers ---------------------------------------------------------------------------
     def _dims(self, bs, n_maps, hf, wf, hd, wd):
@@ -151,6 +152,12 @@ class Mapping(nn.Module):
         ego = ops.map_update(features, depth, gps, compass, masks, full_global_map, e=e, resolution=self.resolution,
                              trig=_trig, scratch=scratch, ego_half=half, env_slots=slots)
         self.last_ego_half = half
+        if self.strict_inputs:
+            flags = ops.env_flags(scratch, dims)
+            bad = (flags & _lib.FLAG_OUTSIDE_FAN).nonzero().flatten().tolist()
+            if bad:
+                raise ValueError(f"envs {bad}: depth < 0 produced cells behind the camera; the B200 kernel drops them "
+                                 "(the reference would scatter them) -- see include/wsmg.h WSMG_FLAG_OUTSIDE_FAN")
         return ego, full_global_map
 
     # -- opt-in extras ---------------------------------------------------------------------
