@@ -135,7 +135,7 @@ def test_strict_inputs_flags_negative_depth():
     depth = make_depth("near", 2, 32, 32, gen)
     obs = dict(depth=depth.to(DEV), gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
     m(feat.to(DEV), obs, torch.zeros(2, 1, device=DEV))                     # fine
-    depth[1, 20:, :, 0] = -0.2                                              # behind the camera: not representable
+    depth[1, :16, :, 0] = -0.2                                              # behind the camera (rows above the horizon pass the height test): not representable
     obs = dict(depth=depth.to(DEV), gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
     with pytest.raises(ValueError, match="envs \\[1\\]"):
         m(feat.to(DEV), obs, torch.ones(2, 1, device=DEV))
