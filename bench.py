@@ -30,7 +30,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SHAPE = dict(C=64, Hf=224, Wf=224, Hd=256, Wd=256, E=100, G=240, resolution=0.12)
+SHAPES = {
+    "real": dict(C=64, Hf=224, Wf=224, Hd=256, Wd=256, E=100, G=240, resolution=0.12),       # the reference's config
+    "b256": dict(C=64, Hf=256, Wf=256, Hd=256, Wd=256, E=100, G=240, resolution=0.12),       # BASELINE.json wording
+    "b256c27": dict(C=27, Hf=256, Wf=256, Hd=256, Wd=256, E=100, G=240, resolution=0.12),    # "reference class count"
+}
+SHAPE = dict(SHAPES["real"])
 DEPTH_KINDS = ("uniform", "near", "room2", "room4")
 
 
@@ -163,7 +168,7 @@ def workload_config(args, world):
     if args.envs:
         total = args.envs
     return {"workload": f"{args.workload}: {total} envs total, {total // world} per GPU, env-sharded, "
-                        f"C=64 feat 224x224 depth 256x256 ego 100 global 240 fp32, depth kinds mixed "
+                        f"C={SHAPE['C']} feat {SHAPE['Hf']}x{SHAPE['Wf']} depth {SHAPE['Hd']}x{SHAPE['Wd']} ego 100 global 240 fp32, depth kinds mixed "
                         f"{'/'.join(DEPTH_KINDS)}, random-walk poses, masks=1 after the first step",
             "envs_total": total, "envs_per_gpu": total // world,
             "l2": "inputs larger than L2 (no flush)" if total // world >= 64 else "L2 flushed between steps",
@@ -386,7 +391,10 @@ def main():
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per k_fused launch from ncu, if known")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-by-depth", action="store_true", help="skip the per-depth-distribution runs")
+    ap.add_argument("--shape", default="real", choices=sorted(SHAPES), help="tensor shapes (secondary shapes of SURVEY 8d)")
     args = ap.parse_args()
+    SHAPE.clear()
+    SHAPE.update(SHAPES[args.shape])
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -219,10 +219,13 @@ static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
     if (rc != 0) return rc;
   }
   p.use_tma = tma ? 1 : 0;
-  const bool ref_shape = vec && p.g.E == 100 && p.g.G == 240 && p.g.Hf * p.g.Wf == 224 * 224;
-  if (ref_shape && !generic) {
+  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !generic;
+  if (ref_geo && p.g.Hf * p.g.Wf == 224 * 224) {          // the reference's shapes (vlnce_task.yaml:11-18)
     return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s)
                : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s);
+  }
+  if (ref_geo && p.g.Hf * p.g.Wf == 256 * 256 && tma) {   // BASELINE.json's wording: features at the depth resolution
+    return launch_fused_t<100, 240, 256 * 256, true, true>(p, grid, s);
   }
   if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s) : launch_fused_t<0, 0, 0, true, false>(p, grid, s);
   return launch_fused_t<0, 0, 0, false, false>(p, grid, s);
