@@ -235,6 +235,22 @@ inline void red_max4(int32_t* cell, int npp, unsigned code, unsigned next, int32
 // bilinear weight is exactly 0 -- its product is an exact 0, so dropping the load is bit-exact for finite data).
 WSMG_HD F4 tap(const F4* base, int idx) { return idx > 0 ? base[idx] : f4_zero(); }
 
+// Lane -> cell mapping of the two rotations.  A warp covers an 8-column x 4-row tile of the E x E grid and
+// each quarter-warp (the unit LDS.128 is issued in) a 4 x 2 block of it: the four bilinear taps of a block
+// land on ~1.6 distinct 16-byte bank groups per wavefront instead of ~2.1 for 8 cells in a row (simulated
+// over random headings and confirmed by ncu), and a row of the tile is still one full 32-byte sector of
+// the NCHW output.  slot = tile * 32 + lane; returns false for the padding of ragged tiles.
+WSMG_HD bool tile_cell(int slot, int E, int* i, int* j) {
+  const int tile = slot >> 5, l = slot & 31;
+  const int tiles_x = (E + 7) >> 3;
+  const int band = tile / tiles_x, tcol = tile - band * tiles_x;
+  const int q = l >> 3, k = l & 7;
+  *j = 8 * tcol + 4 * (q & 1) + (k & 3);
+  *i = 4 * band + 2 * (q >> 1) + (k >> 2);
+  return *j < E && *i < E;
+}
+WSMG_HD int tile_slots(int E) { return ((E + 7) >> 3) * ((E + 3) >> 2) * 32; }
+
 WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const Weights& w) {
   F4 r;
 #pragma unroll
@@ -510,12 +526,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   else { float h = -p.compass[b]; sn = sinf(h); cs = cosf(h); }
   // Cells none of whose taps falls inside the fan (~70 % of the grid) are exact zeros: store and move on.
   // The per-row extent of the other cells lets the fuse step skip window cells that only see zeros.
-  for (int t0 = 0; t0 < EE; t0 += NT) {
-    const int t = t0 + tid;
+  const int nslots = tile_slots(E);
+  for (int s0 = 0; s0 < nslots; s0 += NT) {
+    const int slot = s0 + tid;
     bool hit = false;
     int i = 0, j = 0;
-    if (t < EE) {
-      i = t / E; j = t - i * E;
+    if (slot < nslots && tile_cell(slot, E, &i, &j)) {
+      const int t = i * E + j;
       float ix, iy;
       rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
       Tap1D tx = make_tap(ix), ty = make_tap(iy);
@@ -535,21 +552,20 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       }
     }
 #if defined(__CUDACC__)
-    // a warp covers 32 consecutive cells = at most two rows: one min/max pair per row segment
+    // per-row extents of the warp's 8 x 4 tile: lane r (0..3) owns row r.  Row r's cells sit in lanes
+    // {a_r..a_r+3} (columns 0-3) and {a_r+8..a_r+11} (columns 4-7), a_r = 0, 4, 16, 20.
     const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
     if (m != 0u) {
       const int lane = tid & 31;
-      const int t_first = t - lane, i_first = t_first / E, j_first = t_first - i_first * E;
-      const int split = E - j_first;                         // lanes >= split belong to the next row
-      const unsigned lo_mask = split >= 32 ? 0xFFFFFFFFu : ((1u << split) - 1u);
-      const unsigned m0 = m & lo_mask, m1 = m & ~lo_mask;
-      if (lane == 0 && m0 != 0u) {
-        atomicMin(&ext[i_first].a, j_first + __ffs(m0) - 1);
-        atomicMax(&ext[i_first].b, j_first + 31 - __clz(m0));
-      }
-      if (lane == 1 && m1 != 0u) {
-        atomicMin(&ext[i_first + 1].a, __ffs(m1) - 1 - split);
-        atomicMax(&ext[i_first + 1].b, 31 - __clz(m1) - split);
+      if (lane < 4) {
+        const int a = (lane & 1) * 4 + (lane >> 1) * 16;
+        const unsigned mr = ((m >> a) & 0xFu) | (((m >> (a + 8)) & 0xFu) << 4);
+        if (mr != 0u) {
+          const int tile = (s0 + tid) >> 5, tiles_x = (E + 7) >> 3;
+          const int band = tile / tiles_x, j0 = 8 * (tile - band * tiles_x), row = 4 * band + lane;
+          atomicMin(&ext[row].a, j0 + __ffs(mr) - 1);
+          atomicMax(&ext[row].b, j0 + 31 - __clz(mr));
+        }
       }
     }
 #else
@@ -699,8 +715,10 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   if (p.trig != nullptr) { cs = p.trig[4 * b + 2]; sn = p.trig[4 * b + 3]; }
   else { float h = p.compass[b]; sn = sinf(h); cs = cosf(h); }
   float* ego_b = p.ego + ((size_t)b * C + c0) * EE;
-  for (int t = tid; t < EE; t += NT) {
-    int i = t / E, j = t - i * E;
+  for (int slot = tid; slot < nslots; slot += NT) {
+    int i, j;
+    if (!tile_cell(slot, E, &i, &j)) continue;
+    const int t = i * E + j;
     float ix, iy;
     rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);
     Tap1D tx = make_tap(ix), ty = make_tap(iy);
