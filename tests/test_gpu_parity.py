@@ -256,3 +256,26 @@ def test_kernel_variants_agree():
         assert torch.equal(gmap, ref_map), key
         for a, b in zip(egos, ref_egos):
             assert torch.equal(a, b), key
+
+
+def test_edge_frames_match_oracle():
+    """Empty, far, total-collision, boundary-rounding and NaN/inf depth frames at the real shapes, plus bs = 1."""
+    from edge_frames import edge_depths
+    c, hf, hd = 64, 224, 256
+    gen = torch.Generator().manual_seed(8)
+    for name, depth in edge_depths(hd).items():
+        feat = make_features(1, c, hf, hf, gen, signed=(name == "wall_constant"))
+        gps = torch.tensor([[0.4, -0.3]])
+        compass = torch.tensor([[0.9]])
+        orc = OracleMapper(1, c)
+        orc.full_global_map += 0.25
+        gmap = orc.full_global_map.clone().to(DEV)
+        want = orc.step(feat, depth, gps, compass, torch.ones(1, 1), keep=True)
+        lin, inv = ops.unproject_index(depth.to(DEV), hf, hf)
+        assert torch.equal(lin.cpu().long(), orc.last["lin"]) and torch.equal(inv.cpu(), orc.last["invalid"]), name
+        proj = ops.scatter_max(feat.to(DEV), depth.to(DEV))
+        assert torch.equal(proj.cpu(), orc.last["proj"]), name
+        ego = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), torch.ones(1, 1, device=DEV), gmap,
+                             trig=_trig(compass).to(DEV))
+        assert torch.equal(ego.cpu(), want), name
+        assert torch.equal(gmap.cpu(), orc.full_global_map), name

@@ -160,3 +160,29 @@ def test_half_output_and_env_slots():
     ego_slot, _ = emul_step(g_slot, *f, np.ones((3, 1), np.float32), env_slots=np.array(keep))
     assert np.array_equal(ego_ref, ego_slot)
     assert np.array_equal(g_slot[keep], g_ref2) and np.array_equal(g_slot[1], g_ref[1])   # paused env untouched
+
+
+def test_edge_frames_match_oracle():
+    """Empty, far, total-collision, boundary-rounding and NaN/inf depth frames (SURVEY 8c edge cases)."""
+    from edge_frames import edge_depths
+    from oracle.mapping_oracle import OracleMapper
+    c, hf, hd = 4, 56, 64
+    gen = torch.Generator().manual_seed(8)
+    for name, depth in edge_depths(hd).items():
+        feat = make_features(1, c, hf, hf, gen, signed=True)
+        gps = torch.tensor([[0.4, -0.3]])
+        compass = torch.tensor([[0.9]])
+        orc = OracleMapper(1, c)
+        orc.full_global_map += 0.25                                   # pre-existing map content must survive
+        gmap = orc.full_global_map.numpy().copy()
+        want = orc.step(feat, depth, gps, compass, torch.ones(1, 1), keep=True)
+        lin, inv, _ = emul_cells(depth[..., 0].numpy(), hf)
+        assert np.array_equal(lin, orc.last["lin"].numpy()), name
+        assert np.array_equal(inv, orc.last["invalid"].numpy()), name
+        ego, proj = emul_step(gmap, feat.numpy(), depth[..., 0].numpy(), gps.numpy(), compass.numpy(), np.ones((1, 1), np.float32),
+                              trig=_trig(compass), want_proj=True)
+        assert np.array_equal(proj, orc.last["proj"].numpy()), name
+        assert np.array_equal(ego, want.numpy()), name
+        assert np.array_equal(gmap, orc.full_global_map.numpy()), name
+        if name in ("empty_all_zero", "all_far"):
+            assert not proj.any() and inv.all(), name
