@@ -216,12 +216,11 @@ def test_error_codes():
     x = torch.zeros(16, device=DEV)
     assert lib.wsmg_unproject_index(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(x.data_ptr()),
                                     ctypes.c_void_p(x.data_ptr()), ctypes.byref(bad), None) == -3
-    big = _lib.make_dims(1, 1, 64, 224, 224, 256, 256, 200, 480, 0.12)     # fan + crop do not fit one SM
-    feat = torch.zeros(1, 64, 224, 224, device=DEV)
+    feat = torch.zeros(1, 64, 224, 224, device=DEV)                         # a 120 x 120 crop does not fit one SM's shared memory
     depth = torch.zeros(1, 256, 256, 1, device=DEV)
     with pytest.raises(_lib.WsmgError, match="shared memory"):
         ops.map_update(feat, depth, torch.zeros(1, 2, device=DEV), torch.zeros(1, 1, device=DEV),
-                       torch.zeros(1, 1, device=DEV), torch.zeros(1, 480, 480, 64, device=DEV), e=200)
+                       torch.zeros(1, 1, device=DEV), torch.zeros(1, 300, 300, 64, device=DEV), e=120)
 
 
 def test_kernel_variants_agree():

@@ -282,7 +282,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   const int nch = VEC ? SLAB : ((C - c0) < SLAB ? (C - c0) : SLAB);
   const int paste_lo = G / 2 - E / 2;
   const float half_e = (float)E / 2.0f, half_g = (float)G / 2.0f, gcenter = (float)(G / 2);
-  const int NB = (WW + BAND - 1) / BAND;
+  const int NB = (WW + BAND - 1) / BAND;          // <= MAX_BANDS - 1 (validated on the host)
 
   F4* X = reinterpret_cast<F4*>(smem + sp.x_off);            // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
   int32_t* Pk = reinterpret_cast<int32_t*>(smem + sp.r2_off);
@@ -297,6 +297,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   I2* ext = reinterpret_cast<I2*>(smem + sp.ext_off);         // per R row: [first, last] column with a tap inside the fan
   I2* rowE = fanrow;                                          // per window row: merged extent of its two source R rows (fanrow is dead by then)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);   // one mbarrier per band (TMA)
+  int* chunk_counter = reinterpret_cast<int*>(bars + MAX_BANDS - 1);  // last slot of the barrier array is never a barrier
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63
   float qx = 0.f, qy = 0.f;
@@ -378,7 +379,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
     fanrow[t] = fr;
   }
-  if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); }
+  if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); *chunk_counter = 0; }
   for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
   for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = KEY_EMPTY;
   WSMG_SYNC();
@@ -413,13 +414,31 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       }
       async_commit();                                          // one group per step, live or not: wait counts stay exact
     };
+    // Work distribution: warps pull chunks of 32 consecutive groups from a shared counter (dynamic, so that all
+    // warps reach the barrier together however the valid pixels are distributed); a thread's group in chunk c is
+    // c*CH + lane.  tq[] holds the group indices of the steps in flight.
+    constexpr int CH = NT >= 32 ? 32 : NT;
+    const int lane_c = tid % CH;
+    auto next_group = [&]() -> int {
+      int c = 0;
+#if defined(__CUDACC__)
+      if (lane_c == 0) c = atomicAdd(chunk_counter, 1);
+      c = __shfl_sync(0xFFFFFFFFu, c, 0);
+#else
+      c = (*chunk_counter)++;
+#endif
+      return c * CH + lane_c;
+    };
+    int tq[STAGES + 1];
 #pragma unroll
     for (int s_ = 0; s_ < STAGES; ++s_) {
-      cq[s_] = fetch_codes(tid + s_ * NT);
-      issue(s_, tid + s_ * NT, cq[s_]);
+      tq[s_] = next_group();
+      cq[s_] = fetch_codes(tq[s_]);
+      issue(s_, tq[s_], cq[s_]);
     }
-    cq[STAGES] = fetch_codes(tid + STAGES * NT);
-    for (int t = tid, it = 0; t < n4; t += NT, ++it) {
+    tq[STAGES] = next_group();
+    cq[STAGES] = fetch_codes(tq[STAGES]);
+    for (int it = 0; tq[0] - lane_c < n4; ++it) {             // warp-uniform: chunk start < n4
       const int slot = it % STAGES;
       const uint2 cc = cq[0];
       async_wait<STAGES - 1>();                                // this group's copies have landed
@@ -460,11 +479,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
           }
         }
       }
-      // refill the slot just consumed with the group STAGES steps ahead; advance the code queue
+      // refill the slot just consumed with the group STAGES steps ahead; advance the queues
 #pragma unroll
-      for (int s_ = 0; s_ < STAGES; ++s_) cq[s_] = cq[s_ + 1];
-      issue(slot, t + STAGES * NT, cq[STAGES - 1]);
-      cq[STAGES] = fetch_codes(t + (STAGES + 1) * NT);
+      for (int s_ = 0; s_ < STAGES; ++s_) { cq[s_] = cq[s_ + 1]; tq[s_] = tq[s_ + 1]; }
+      issue(slot, tq[STAGES - 1], cq[STAGES - 1]);
+      tq[STAGES] = next_group();
+      cq[STAGES] = fetch_codes(tq[STAGES]);
     }
     async_wait<0>();
   }

@@ -18,7 +18,7 @@ inline int validate_dims(const wsmg_dims* d) {
   if (d->E > d->G) return WSMG_E_EGO_GT_GLOBAL;
   if (d->n_maps < d->bs) return WSMG_E_BATCH;
   if ((d->Hf * d->Wf) % 4 != 0) return WSMG_E_ALIGN;
-  if (d->E > 254 || d->G > 32768) return WSMG_E_DIMS;          // packed fan codes are 16 bit
+  if (d->E > 126 || d->G > 32768) return WSMG_E_DIMS;          // 16-bit fan codes; (E+2)/9 bands must fit the barrier array
   return WSMG_OK;
 }
 
