@@ -17,7 +17,7 @@
 
 namespace wsmg {
 
-constexpr int FUSED_THREADS = 1024;
+constexpr int FUSED_THREADS = FUSED_NT;
 constexpr int CELLS_THREADS = 256;
 
 // ------------------------------------------------------------------ k_reset

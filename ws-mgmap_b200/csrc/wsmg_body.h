@@ -41,6 +41,8 @@
 namespace wsmg {
 
 constexpr int SLAB = 4;            // channels per CTA
+constexpr int FUSED_NT = 1024;     // threads of a k_fused CTA
+constexpr int SCATTER_STAGES = 2;  // cp.async feature slots per thread (staged in X, which is idle during the scatter)
 constexpr int BAND = 9;            // window rows per fuse band
 constexpr int NEG = -(1 << 24);    // "tap out of range": any index sum containing it is negative
 
@@ -97,7 +99,9 @@ WSMG_HD SmemPlan make_plan(const Geo& g) {
   s.s0 = (s.npp + s.wwp - 1) / s.wwp;
   s.rr = 4 * BAND + 2 > s.s0 + BAND ? 4 * BAND + 2 : s.s0 + BAND;
   s.x_off = 0;
-  s.r2_off = ((1 + g.E * g.E) * 16 + 16 + 127) & ~127;      // 128-byte aligned: TMA destination rows
+  int x_cells = 1 + g.E * g.E;                               // X also hosts the scatter's staging slots
+  if (x_cells < 1 + SCATTER_STAGES * SLAB * FUSED_NT) x_cells = 1 + SCATTER_STAGES * SLAB * FUSED_NT;
+  s.r2_off = (x_cells * 16 + 16 + 127) & ~127;               // 128-byte aligned: TMA destination rows
   s.z_off = s.r2_off - 16;
   s.tab_off = s.r2_off + s.rr * s.wwp * 16;
   s.base_off = s.tab_off + (2 * WW + 2 * g.E) * 16;
@@ -396,7 +400,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     // Codes run STAGES steps ahead of the features, so their L2 latency never sits in front of a feature copy.
     // Valid pixels carry a fan cell (< CODE_OUTLIER): every u16 lane of (x & y) has its top 15 bits set iff none of
     // the four pixels writes -- such a group skips its feature read.
-    constexpr int STAGES = 2;
+    constexpr int STAGES = SCATTER_STAGES;
+    static_assert(NT <= FUSED_NT, "staging slots are sized for FUSED_NT threads");
     F4* stage = X + 1;                                        // [STAGES][SLAB][NT]
     uint2 cq[STAGES + 1];                                     // codes of the groups in flight (+1: next to be issued)
     auto fetch_codes = [&](int tt) -> uint2 {
