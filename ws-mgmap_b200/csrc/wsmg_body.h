@@ -3,19 +3,23 @@
 //   * by g++ as a serial emulation (wsmg_emul.cpp, NT = 1) that the CPU tests compare against
 //     the oracle.  The emulation is test infrastructure; nothing in the product path calls it.
 //
-// The kernel is instruction-issue bound before it is HBM bound (ncu, profiles/), so the code
-// trades shared-memory tables and compile-time constants for instructions everywhere:
-//   * CTA size, ego/global size and the feature-plane stride are template constants for the
-//     reference shapes; single-trip loops collapse to an `if`, divisions to multiplies, channel
-//     plane offsets to immediates;
-//   * every bilinear tap is `table entry + table entry -> max(.,0) -> LDS.128`; index 0 of X
-//     and of the fan / F ring is a zero cell that every out-of-range tap resolves to;
-//   * the scatter keeps per-value work branch-free (select, max, 2-op key, predicated ATOMS).
+// Design rules that came out of the ncu captures under profiles/ (the kernel was, in turn, instruction-issue
+// bound, LSU-wavefront bound and finally latency/barrier bound at the 32 warps one 231 KB CTA leaves an SM):
+//   * CTA size, ego/global size and the feature-plane stride are template constants for the reference
+//     shapes; single-trip loops collapse to an `if`, divisions to multiplies, plane offsets to immediates;
+//   * every bilinear tap is `table entry + table entry -> LDS.128`, index <= 0 meaning "zero": out-of-range
+//     taps, taps whose weight is exactly 0 (two thirds of the translate rows/columns) and taps outside the
+//     fan are never read;
+//   * the NHWC map window moves with TMA row boxes (no LSU), the feature planes with per-thread cp.async
+//     slots staged in the not-yet-used X buffer;
+//   * the scatter reduces runs of equal cells in registers and issues plain shared atomics on signed keys
+//     for which a non-negative float is its own key (profiles/: match_any+redux aggregation is 39x slower).
 //
-// Shared memory (E=100, G=240: 229.7 KB of the 227 KiB = 232448 B a CTA may opt in to):
-//   X     [1 + E*E] F4    zero cell + rotated ego grid R; rows are overwritten by the crop B
+// Shared memory (E=100, G=240: 231968 of the 232448 bytes a CTA may opt in to):
+//   X     [1 + E*E] F4    zero cell + (during the scatter) the per-thread cp.async feature slots, then the
+//                         rotated ego grid R; its rows are overwritten by the crop B behind the fuse front
 //   Z     1 F4            zero cell shared by the fan and the F ring (sits right before R2)
-//   R2    scatter: planar u32 keys [4][npp], then F4[fan_cells];
+//   R2    scatter: planar signed-int keys [4][npp], then F4[fan_cells];
 //         afterwards: F ring, `rr` window rows of WWP cells (128-byte aligned rows).  Each row of
 //         the caller's map window is a TMA box {4 ch, WW cols, 1 row} copied straight into its
 //         ring row (mbarrier complete_tx; out-of-map cells arrive as zeros), max-fused IN PLACE
@@ -23,7 +27,7 @@
 //         never touches the LSU.  Band 0 lands beyond the key planes so that it streams in
 //         underneath the scatter.  (C % 4 != 0: cp.async / st.global fallback.)
 //   T     colT[WW], rowT[WW], bXT[E], bYT[E] (I4 each): the two separable translations
-//   tail  baseE[E], fanrow[E+1], flags
+//   tail  baseE[E], fanrow[E+1] (later rowE[E+2]), ext[E], mbarriers + the scatter's chunk counter
 #pragma once
 #include "wsmg_math.h"
 #if defined(__CUDACC__)
@@ -192,17 +196,6 @@ template <int N> __device__ __forceinline__ void tma_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-// four predicated shared-memory max-reductions (one per channel plane), predicate evaluated in PTX:
-// the pixel writes (code < 0xFFFE) and closes its run (code != next).  No branch, no predicate spill.
-__device__ __forceinline__ void red_max4(int32_t* cell, int npp, unsigned code, unsigned next,
-                                         int32_t k0, int32_t k1, int32_t k2, int32_t k3) {
-  unsigned a = saddr(cell);
-  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %4, %5;\n setp.lt.and.u32 p, %4, 0xFFFE, p;\n"
-               " @p red.shared.max.s32 [%0], %6;\n @p red.shared.max.s32 [%1], %7;\n"
-               " @p red.shared.max.s32 [%2], %8;\n @p red.shared.max.s32 [%3], %9;\n}\n"
-               ::"r"(a), "r"(a + 4 * npp), "r"(a + 8 * npp), "r"(a + 12 * npp), "r"(code), "r"(next),
-                 "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
-}
 #else
 inline void smem_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
 inline F4 ld_stream4(const float* p) { F4 r; for (int i = 0; i < 4; ++i) r.v[i] = p[i]; return r; }
@@ -228,11 +221,6 @@ inline void tma_store_row(const void*, int, int, int, int, const void*) {}
 inline void tma_commit() {}
 template <int N> inline void tma_wait_read() {}
 inline void fence_proxy_async() {}
-inline void red_max4(int32_t* cell, int npp, unsigned code, unsigned next, int32_t k0, int32_t k1, int32_t k2, int32_t k3) {
-  if (code < 0xFFFEu && code != next) {
-    smem_max(cell, k0); smem_max(cell + npp, k1); smem_max(cell + 2 * npp, k2); smem_max(cell + 3 * npp, k3);
-  }
-}
 #endif
 
 // Tap that skips the shared-memory read when the index says "zero cell" (out of range, or a tap whose
