@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WSMG_ABI_VERSION 1
+#define WSMG_ABI_VERSION 2
 
 enum {
   WSMG_OK = 0,
@@ -49,6 +49,10 @@ typedef struct wsmg_dims {
   int32_t E;       /* egocentric_map_size (100)                                    */
   int32_t G;       /* global_map_size (240)                                        */
   double resolution; /* metres per cell (0.12)                                      */
+  int32_t C_in;    /* channels of `feat` (0 = C).  C_in != C: the channel re-binning of
+                      RGBMapping.forward (adaptive_max_pool1d over channels, rgb_mapping.py:81-84)
+                      is applied inside the scatter: output channel k = max over input channels
+                      [floor(k*C_in/C), ceil((k+1)*C_in/C)).                       */
 } wsmg_dims;
 
 int wsmg_abi_version(void);
@@ -69,7 +73,7 @@ size_t wsmg_scratch_flags_offset(const wsmg_dims* d);
 
 /* Whole step: Mapping.project_feat_to_map (rgb_mapping.py:32-72) as called by
  * RGBMapping.forward (rgb_mapping.py:85).
- *   feat     [bs,C,Hf,Wf] fp32 NCHW          (rgb_features after the identity channel pool, :81-84)
+ *   feat     [bs,C_in,Hf,Wf] fp32 NCHW       (rgb_features as the UNet emits them; channel pool of :81-84 fused)
  *   depth    [bs,Hd,Wd,1] fp32 in [0,1]      (observations['depth']; the x10 of :37 is applied inside)
  *   gps      [bs,2], compass [bs,1], mask [bs,1] fp32
  *   gmap     [n_maps,G,G,C] fp32 NHWC        (self.full_global_map; rows [:bs] updated in place, :35,:56)

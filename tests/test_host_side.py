@@ -23,7 +23,7 @@ def test_library_exports_header_symbols():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/wsmg.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.wsmg_abi_version() == 1
+    assert lib.wsmg_abi_version() == 2
     assert b"NULL" in lib.wsmg_error_string(-1)
 
 

@@ -186,3 +186,23 @@ def test_edge_frames_match_oracle():
         assert np.array_equal(gmap, orc.full_global_map.numpy()), name
         if name in ("empty_all_zero", "all_far"):
             assert not proj.any() and inv.all(), name
+
+
+@pytest.mark.parametrize("c_in,c_out", [(8, 4), (10, 4), (7, 3), (3, 5), (64, 27)])
+def test_fused_channel_pool(c_in, c_out):
+    """RGBMapping.forward's adaptive_max_pool1d over channels (rgb_mapping.py:81-84), fused into the scatter."""
+    from oracle.mapping_oracle import OracleMapper
+    bs, hf, hd = 2, 24, 32
+    gen = torch.Generator().manual_seed(c_in * 100 + c_out)
+    feat = make_features(bs, c_in, hf, hf, gen, signed=True)
+    depth = make_depth("near", bs, hd, hd, gen)
+    gps, compass = torch.randn(bs, 2, generator=gen), torch.rand(bs, 1, generator=gen) * 6 - 3
+    pooled = torch.nn.functional.adaptive_max_pool1d(feat.permute(0, 2, 3, 1).reshape(bs, -1, c_in), c_out)
+    pooled = pooled.reshape(bs, hf, hf, c_out).permute(0, 3, 1, 2).contiguous()
+    orc = OracleMapper(bs, c_out)
+    want = orc.step(pooled, depth, gps, compass, torch.zeros(bs, 1), keep=True)
+    gmap = np.zeros((bs, 240, 240, c_out), np.float32)
+    ego, proj = emul_step(gmap, feat.numpy(), depth[..., 0].numpy(), gps.numpy(), compass.numpy(), np.zeros((bs, 1), np.float32),
+                          trig=_trig(compass), want_proj=True, map_depth=c_out)
+    assert np.array_equal(proj, orc.last["proj"].numpy())
+    assert np.array_equal(ego, want.numpy()) and np.array_equal(gmap, orc.full_global_map.numpy())

@@ -13,7 +13,7 @@ class WsmgDims(ctypes.Structure):
     _fields_ = [
         ("bs", ctypes.c_int32), ("n_maps", ctypes.c_int32), ("C", ctypes.c_int32),
         ("Hf", ctypes.c_int32), ("Wf", ctypes.c_int32), ("Hd", ctypes.c_int32), ("Wd", ctypes.c_int32),
-        ("E", ctypes.c_int32), ("G", ctypes.c_int32), ("resolution", ctypes.c_double),
+        ("E", ctypes.c_int32), ("G", ctypes.c_int32), ("resolution", ctypes.c_double), ("C_in", ctypes.c_int32),
     ]
 
 
@@ -65,8 +65,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.wsmg_abi_version() != 1:
-        raise WsmgError(f"libwsmg ABI {lib.wsmg_abi_version()} != 1")
+    if lib.wsmg_abi_version() != 2:
+        raise WsmgError(f"libwsmg ABI {lib.wsmg_abi_version()} != 2")
     _lib = lib
     return lib
 
@@ -77,5 +77,6 @@ def check(rc: int, what: str) -> None:
         raise WsmgError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
 
 
-def make_dims(bs, n_maps, c, hf, wf, hd, wd, e, g, resolution) -> WsmgDims:
-    return WsmgDims(int(bs), int(n_maps), int(c), int(hf), int(wf), int(hd), int(wd), int(e), int(g), float(resolution))
+def make_dims(bs, n_maps, c, hf, wf, hd, wd, e, g, resolution, c_in=0) -> WsmgDims:
+    return WsmgDims(int(bs), int(n_maps), int(c), int(hf), int(wf), int(hd), int(wd), int(e), int(g), float(resolution),
+                    int(c_in))

@@ -219,7 +219,7 @@ static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
     if (rc != 0) return rc;
   }
   p.use_tma = tma ? 1 : 0;
-  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !generic;
+  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !generic;      // (any Cin: the pool is a run-time branch)
   if (ref_geo && p.g.Hf * p.g.Wf == 224 * 224) {          // the reference's shapes (vlnce_task.yaml:11-18)
     return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s)
                : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s);
@@ -364,7 +364,7 @@ static size_t slot_bytes(const wsmg_dims* d, int chunk, HostSlot* out, unsigned 
   wsmg_dims dc = *d; dc.bs = chunk; dc.n_maps = chunk > d->n_maps ? chunk : d->n_maps;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  size_t o_feat = take((size_t)chunk * d->C * d->Hf * d->Wf * 4);
+  size_t o_feat = take((size_t)chunk * (d->C_in > 0 ? d->C_in : d->C) * d->Hf * d->Wf * 4);
   size_t o_depth = take((size_t)chunk * d->Hd * d->Wd * 4);
   size_t o_gps = take((size_t)chunk * 2 * 4);
   size_t o_comp = take((size_t)chunk * 4);
@@ -418,7 +418,7 @@ int wsmg_map_update_host(const float* feat_host, const float* depth_host, const 
     HostSlot hs;
     slot_bytes(d, chunk, &hs, (unsigned char*)staging + slot * one);
     cudaStream_t s = st[slot];
-    const size_t fe = (size_t)d->C * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
+    const size_t fe = (size_t)(d->C_in > 0 ? d->C_in : d->C) * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
     cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s);

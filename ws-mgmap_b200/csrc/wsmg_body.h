@@ -379,8 +379,29 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // ---- phase 1: scatter-max into the packed fan (rgb_mapping.py:210-225) -----------------------
   if (p.proj_in == nullptr) {
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
-    const float* plane0 = p.feat + ((size_t)b * C + c0) * HW;
+    // Channel pool (rgb_mapping.py:81-84) fused: when Cin != C the scatter runs once per input plane of a bin,
+    // all passes reducing into the same key plane (max over channels commutes with the max-scatter).
+    const int Cin = g.Cin;
+    const bool pool = Cin != C;
+    int bin_lo[SLAB], bin_n[SLAB], passes = 1;
+#pragma unroll
+    for (int ch = 0; ch < SLAB; ++ch) {
+      const int k = c0 + (ch < nch ? ch : 0);
+      bin_lo[ch] = pool ? pool_start(k, Cin, C) : k;
+      bin_n[ch] = pool ? pool_end(k, Cin, C) - bin_lo[ch] : 1;
+      passes = bin_n[ch] > passes ? bin_n[ch] : passes;
+    }
+    const float* feat_b = p.feat + (size_t)b * Cin * HW;
     const int n4 = HW / 4;
+    for (int pass = 0; pass < passes; ++pass) {
+    size_t plane_off[SLAB];                                   // element offset of this pass's input plane per output channel
+#pragma unroll
+    for (int ch = 0; ch < SLAB; ++ch) plane_off[ch] = (size_t)(bin_lo[ch] + (pass < bin_n[ch] ? pass : bin_n[ch] - 1)) * HW;
+    if (pass > 0) {                                           // all warps done with the previous pass: restart the chunk counter
+      WSMG_SYNC();
+      if (tid == 0) *chunk_counter = 0;
+      WSMG_SYNC();
+    }
     // Feature staging through shared memory: X is idle until phase 2, so every thread owns STAGES private
     // 64-byte slots in it ([slot][channel][thread] float4s: conflict-free) and keeps STAGES groups (4 pixels x 4
     // channels) in flight with cp.async while it reduces the oldest one -- no registers are tied up by loads in
@@ -400,10 +421,10 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     auto is_live = [](uint2 c) { return ((c.x & c.y) | 0x00010001u) != 0xFFFFFFFFu; };   // (codes past the end are 0xFFFF)
     auto issue = [&](int slot, int tt, uint2 c) {
       if (is_live(c)) {
-        const float* src = plane0 + 4 * (size_t)tt;
+        const float* src = feat_b + 4 * (size_t)tt;
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
-          if (ch < nch) async_copy16(stage + (slot * SLAB + ch) * NT + tid, src + (size_t)ch * HW, true);
+          if (ch < nch) async_copy16(stage + (slot * SLAB + ch) * NT + tid, src + (pool ? plane_off[ch] : (size_t)(c0 + ch) * HW), true);
       }
       async_commit();                                          // one group per step, live or not: wait counts stay exact
     };
@@ -480,6 +501,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       cq[STAGES] = fetch_codes(tq[STAGES]);
     }
     async_wait<0>();
+    }   // pass
   }
   WSMG_SYNC();
 

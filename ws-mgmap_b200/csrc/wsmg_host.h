@@ -17,6 +17,7 @@ inline int validate_dims(const wsmg_dims* d) {
   if (d->Hd != d->Wd || d->Hf != d->Wf) return WSMG_E_DIMS;   // the reference assumes square frames (rgb_mapping.py:149-151,189)
   if (d->E > d->G) return WSMG_E_EGO_GT_GLOBAL;
   if (d->n_maps < d->bs) return WSMG_E_BATCH;
+  if (d->C_in < 0) return WSMG_E_CHANNELS;
   if ((d->Hf * d->Wf) % 4 != 0) return WSMG_E_ALIGN;
   if (d->E > 126 || d->G > 32768) return WSMG_E_DIMS;          // 16-bit fan codes; (E+2)/9 bands must fit the barrier array
   return WSMG_OK;
@@ -24,6 +25,7 @@ inline int validate_dims(const wsmg_dims* d) {
 
 inline Geo make_geo(const wsmg_dims* d) {
   Geo g;
+  g.Cin = d->C_in > 0 ? d->C_in : d->C;
   g.E = d->E; g.G = d->G; g.C = d->C; g.Hf = d->Hf; g.Wf = d->Wf; g.Hd = d->Hd; g.Wd = d->Wd;
   const double cmin = -(double)d->G * d->resolution / 2;       // rgb_mapping.py:21
   const double cmax = (double)d->G * d->resolution / 2;        // rgb_mapping.py:22

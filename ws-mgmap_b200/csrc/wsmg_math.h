@@ -24,6 +24,7 @@ constexpr float SENTINEL = -1e16f;           // rgb_mapping.py:187
 // ---------------------------------------------------------------- geometry constants
 struct Geo {
   int E, G, C, Hf, Wf, Hd, Wd;
+  int Cin;               // channels of the feature tensor (== C unless the channel pool of rgb_mapping.py:81-84 applies)
   int paste_lo;          // G/2 - floor(E/2)                      rgb_mapping.py:42
   int fan_rows;          // rows of the ego grid a depth >= 0 pixel can reach
   int fan_cells;         // packed cells of the fan
@@ -52,6 +53,11 @@ WSMG_HD int fan_row_width(int y, int E) {
 WSMG_HD int fan_row_offset(int y, int E) {
   return y <= 3 ? y * E : 3 * E + (y - 3) * (E + 4) - (y - 1) * y + 6;
 }
+
+// adaptive_max_pool1d bins over the channel axis (ATen adaptive pooling): output channel k covers input
+// channels [floor(k*Cin/C), ceil((k+1)*Cin/C)).
+WSMG_HD int pool_start(int k, int Cin, int C) { return (int)(((long long)k * Cin) / C); }
+WSMG_HD int pool_end(int k, int Cin, int C) { return (int)((((long long)(k + 1)) * Cin + C - 1) / C); }
 
 // ---------------------------------------------------------------- order-preserving keys
 // Signed 32-bit keys whose integer order is the float order: a non-negative float is its own bit pattern

@@ -18,9 +18,11 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def dims_for(feat_shape, depth_shape, n_maps, e=100, g=240, resolution=0.12):
-    bs, c, hf, wf = feat_shape
-    return _lib.make_dims(bs, n_maps, c, hf, wf, depth_shape[1], depth_shape[2], e, g, resolution)
+def dims_for(feat_shape, depth_shape, n_maps, e=100, g=240, resolution=0.12, map_depth=None):
+    """map_depth: channels of the map when they differ from the features' (channel pool fused in the kernel)."""
+    bs, c_in, hf, wf = feat_shape
+    c = c_in if map_depth is None else map_depth
+    return _lib.make_dims(bs, n_maps, c, hf, wf, depth_shape[1], depth_shape[2], e, g, resolution, c_in=0 if c == c_in else c_in)
 
 
 def scratch_bytes(dims) -> int:
@@ -41,11 +43,11 @@ def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, tr
     env_slots: optional int32 [bs] map row per frame (see include/wsmg.h wsmg_opts)."""
     lib = _lib.load()
     dev = gmap.device
-    d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution)
+    d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution, map_depth=gmap.shape[3])
     if scratch is None:
         scratch = alloc_scratch(d, dev)
     if ego is None:
-        ego = torch.empty(feat.shape[0], feat.shape[1], e, e, device=dev, dtype=torch.float32)
+        ego = torch.empty(feat.shape[0], gmap.shape[3], e, e, device=dev, dtype=torch.float32)
     if ego_half is not None and (ego_half.dtype != torch.float16 or tuple(ego_half.shape) != tuple(ego.shape)):
         raise ValueError("ego_half must be a float16 tensor shaped like the ego map")
     if env_slots is not None and (env_slots.dtype != torch.int32 or env_slots.numel() != feat.shape[0]):
@@ -79,13 +81,13 @@ def unproject_index(depth, hf, wf, e=100, g=240, resolution=0.12):
     return lin, inv.bool()
 
 
-def scatter_max(feat, depth, e=100, g=240, resolution=0.12):
-    """-> proj_feats [bs,C,E,E] (before rotation)."""
+def scatter_max(feat, depth, e=100, g=240, resolution=0.12, map_depth=None):
+    """-> proj_feats [bs,C,E,E] (before rotation); map_depth != feat channels applies the fused channel pool."""
     lib = _lib.load()
     dev = feat.device
-    d = dims_for(feat.shape, depth.shape, feat.shape[0], e, g, resolution)
+    d = dims_for(feat.shape, depth.shape, feat.shape[0], e, g, resolution, map_depth=map_depth)
     scratch = alloc_scratch(d, dev)
-    proj = torch.empty(feat.shape[0], feat.shape[1], e, e, device=dev, dtype=torch.float32)
+    proj = torch.empty(feat.shape[0], d.C, e, e, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         rc = lib.wsmg_scatter_max(_ptr(feat), _ptr(depth), _ptr(proj), _ptr(scratch), scratch.numel(),
                                   ctypes.byref(d), _stream(dev))

@@ -95,9 +95,10 @@ class Mapping(nn.Module):
         self.strict_inputs = False   # debugging aid: synchronise after each update and raise if a valid pixel was dropped
 
     # -- helpers ---------------------------------------------------------------------------
-    def _dims(self, bs, n_maps, hf, wf, hd, wd):
-        return _lib.make_dims(bs, n_maps, self.global_map_depth, hf, wf, hd, wd,
-                              self.egocentric_map_size, self.global_map_size, self.resolution)
+    def _dims(self, bs, n_maps, hf, wf, hd, wd, c_in):
+        c = self.global_map_depth
+        return _lib.make_dims(bs, n_maps, c, hf, wf, hd, wd, self.egocentric_map_size, self.global_map_size,
+                              self.resolution, c_in=0 if c_in == c else c_in)
 
     def _scratch_for(self, dims, device):
         need = self._lib.wsmg_scratch_bytes(ctypes.byref(dims))
@@ -130,9 +131,7 @@ class Mapping(nn.Module):
         if tuple(full_global_map.shape[1:]) != (g, g, c):
             raise ValueError(f"full_global_map has shape {tuple(full_global_map.shape)}, expected [n,{g},{g},{c}]")
         features = self._f32c(features, "features", dev)
-        bs, cf, hf, wf = features.shape
-        if cf != c:
-            raise ValueError(f"features have {cf} channels, map_depth is {c}")
+        bs, cf, hf, wf = features.shape          # cf != c: the channel pool of rgb_mapping.py:81-84 runs inside the kernel
         if bs > full_global_map.shape[0]:
             raise ValueError(f"batch {bs} larger than the map state ({full_global_map.shape[0]} envs)")
         depth = self._f32c(observations["depth"], "observations['depth']", dev)
@@ -143,7 +142,7 @@ class Mapping(nn.Module):
         masks = self._f32c(masks, "masks", dev)
         if gps.shape != (bs, 2) or compass.numel() != bs or masks.numel() != bs:
             raise ValueError("gps must be [bs,2], compass [bs,1], masks [bs,1]")
-        dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2])
+        dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2], cf)
         scratch = self._scratch_for(dims, dev)
         slots = self.env_slots
         if slots is not None and slots.numel() != bs:
@@ -195,13 +194,8 @@ class RGBMapping(Mapping):
         """rgb_mapping.py:79-90: returns the cached ego map when the observations already carry
         one (LMDB replay, unet_encoder.py:65-66); otherwise one map update."""
         if 'rgb_ego_map' not in observations:
-            c_in = rgb_features.shape[1]
-            if c_in != self.global_map_depth:
-                # channel re-binning of rgb_mapping.py:82-84 (identity when C_in == map_depth, the shipped config)
-                bs, _, h, w = rgb_features.shape
-                x = rgb_features.permute(0, 2, 3, 1).reshape(bs, -1, c_in)
-                x = F.adaptive_max_pool1d(x, self.global_map_depth)
-                rgb_features = x.reshape(bs, h, w, -1).permute(0, 3, 1, 2)
+            # The channel re-binning of rgb_mapping.py:82-84 (adaptive_max_pool1d over channels; identity when
+            # C_in == map_depth, the shipped config) is fused into the kernel's scatter: features go in as they are.
             final_retrieval, self.full_global_map = self.project_feat_to_map(
                 rgb_features, self.full_global_map, observations, masks)
             observations['rgb_ego_map'] = final_retrieval
