@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
 }
 
 // ------------------------------------------------------------------ k_fused
-template <int CE, int CG, int CHW, bool VEC, bool TMA>
+template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  fused_body<FUSED_THREADS, CE, CG, CHW, VEC, TMA>(p, blockIdx.x, smem, threadIdx.x);
+  fused_body<FUSED_THREADS, CE, CG, CHW, VEC, TMA, POOL>(p, blockIdx.x, smem, threadIdx.x);
 }
 
 // ------------------------------------------------------------------ host glue
@@ -190,11 +190,11 @@ static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const 
   return 0;
 }
 
-template <int CE, int CG, int CHW, bool VEC, bool TMA>
+template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL = false>
 static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
   if (e != cudaSuccess) return (int)e;
-  k_fused<CE, CG, CHW, VEC, TMA><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
+  k_fused<CE, CG, CHW, VEC, TMA, POOL><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -219,7 +219,11 @@ static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
     if (rc != 0) return rc;
   }
   p.use_tma = tma ? 1 : 0;
-  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !generic;      // (any Cin: the pool is a run-time branch)
+  if (p.g.Cin != p.g.C) {                                   // channel pool fused in the scatter: run-time geometry builds
+    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s);
+    return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s);
+  }
+  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !generic;
   if (ref_geo && p.g.Hf * p.g.Wf == 224 * 224) {          // the reference's shapes (vlnce_task.yaml:11-18)
     return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s)
                : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s);

@@ -255,7 +255,8 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 // at compile time (the reference's 100 / 240 / 224*224); 0: read from p.g.
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
 // TMA: the map window moves through cp.async.bulk.tensor (needs VEC); else cp.async + st.global.
-template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA_BUILD>
+// POOL: feature channels != map channels, the channel pool of rgb_mapping.py:81-84 runs inside the scatter.
+template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA_BUILD, bool POOL>
 WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, const int tid) {
   const Geo& g = p.g;
   const SmemPlan& sp = p.sp;
@@ -382,7 +383,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     // Channel pool (rgb_mapping.py:81-84) fused: when Cin != C the scatter runs once per input plane of a bin,
     // all passes reducing into the same key plane (max over channels commutes with the max-scatter).
     const int Cin = g.Cin;
-    const bool pool = Cin != C;
+    constexpr bool pool = POOL;
     int bin_lo[SLAB], bin_n[SLAB], passes = 1;
 #pragma unroll
     for (int ch = 0; ch < SLAB; ++ch) {
