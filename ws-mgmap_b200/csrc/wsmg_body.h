@@ -413,7 +413,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     constexpr int STAGES = SCATTER_STAGES;
     static_assert(NT <= FUSED_NT, "staging slots are sized for FUSED_NT threads");
     F4* stage = X + 1;                                        // [STAGES][SLAB][NT]
-    uint2 cq[STAGES + 1];                                     // codes of the groups in flight (+1: next to be issued)
+    constexpr int QD = STAGES + 3;                            // queue depth: the codes run 3 steps ahead of the feature copies,
+    uint2 cq[QD];                                             // so even the short iterations of the dead zone hide their L2 latency
     auto fetch_codes = [&](int tt) -> uint2 {
       uint2 c; c.x = c.y = 0xFFFFFFFFu;
       if (tt < n4) c = ld_codes(codes4 + tt);
@@ -444,15 +445,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #endif
       return c * CH + lane_c;
     };
-    int tq[STAGES + 1];
+    int tq[QD];
 #pragma unroll
-    for (int s_ = 0; s_ < STAGES; ++s_) {
+    for (int s_ = 0; s_ < QD; ++s_) {
       tq[s_] = next_group();
       cq[s_] = fetch_codes(tq[s_]);
-      issue(s_, tq[s_], cq[s_]);
     }
-    tq[STAGES] = next_group();
-    cq[STAGES] = fetch_codes(tq[STAGES]);
+#pragma unroll
+    for (int s_ = 0; s_ < STAGES; ++s_) issue(s_, tq[s_], cq[s_]);
     for (int it = 0; tq[0] - lane_c < n4; ++it) {             // warp-uniform: chunk start < n4
       const int slot = it % STAGES;
       const uint2 cc = cq[0];
@@ -496,10 +496,10 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       }
       // refill the slot just consumed with the group STAGES steps ahead; advance the queues
 #pragma unroll
-      for (int s_ = 0; s_ < STAGES; ++s_) { cq[s_] = cq[s_ + 1]; tq[s_] = tq[s_ + 1]; }
+      for (int s_ = 0; s_ + 1 < QD; ++s_) { cq[s_] = cq[s_ + 1]; tq[s_] = tq[s_ + 1]; }
       issue(slot, tq[STAGES - 1], cq[STAGES - 1]);
-      tq[STAGES] = next_group();
-      cq[STAGES] = fetch_codes(tq[STAGES]);
+      tq[QD - 1] = next_group();
+      cq[QD - 1] = fetch_codes(tq[QD - 1]);
     }
     async_wait<0>();
     }   // pass
