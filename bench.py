@@ -169,7 +169,7 @@ def workload_config(args, world):
         total = args.envs
     return {"workload": f"{args.workload}: {total} envs total, {total // world} per GPU, env-sharded, "
                         f"C={SHAPE['C']} feat {SHAPE['Hf']}x{SHAPE['Wf']} depth {SHAPE['Hd']}x{SHAPE['Wd']} ego 100 global 240 fp32, depth kinds mixed "
-                        f"{'/'.join(DEPTH_KINDS)}, random-walk poses, masks=1 after the first step",
+                        f"{'/'.join(DEPTH_KINDS)}, random-walk poses, a new frame per env per step, masks=1 after the first step",
             "envs_total": total, "envs_per_gpu": total // world,
             "l2": "inputs larger than L2 (no flush)" if total // world >= 64 else "L2 flushed between steps",
             "bytes_per_frame_algorithmic": algorithmic_bytes_per_frame()}
@@ -197,12 +197,17 @@ def run_native(args, rank, local_rank, world):
 
     # ---- synthetic inputs, resident in HBM --------------------------------------------------
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    feat = torch.rand(n, s["C"], s["Hf"], s["Wf"], generator=gen, device=dev)
+    # Every env sees a NEW frame every step, as in a rollout: n + T frames are resident and step t reads the
+    # window [t, t+n).  (Re-feeding the same frame would leave the max-fused map unchanged after a few steps,
+    # and a map update that changes nothing also writes nothing.)
+    T = W + 2 * K
+    feat_all = torch.rand(n + T, s["C"], s["Hf"], s["Wf"], generator=gen, device=dev)
     cgen = torch.Generator().manual_seed(99 + rank)
     kinds = [make_depth(k, 8, s["Hd"], s["Wd"], cgen) for k in DEPTH_KINDS]
-    depth = torch.stack([kinds[b % 4][(b // 4) % 8] for b in range(n)], 0).to(dev).contiguous()
+    depth_all = torch.stack([kinds[b % 4][(b // 4) % 8] for b in range(n + T)], 0).to(dev).contiguous()
+    feat, depth = feat_all[:n], depth_all[:n]
     walk = RandomWalk(n, seed=7 + rank)
-    poses = [walk.step() for _ in range(W + K)]
+    poses = [walk.step() for _ in range(T)]
     gps = torch.stack([p[0] for p in poses]).to(dev)
     compass = torch.stack([p[1] for p in poses]).to(dev)
     masks = torch.stack([p[2] for p in poses]).to(dev)
@@ -216,6 +221,7 @@ def run_native(args, rank, local_rank, world):
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
 
     def step(t, ev0=None, ev1=None):
+        feat, depth = feat_all[t:t + n], depth_all[t:t + n]
         if ev0 is None:
             rc = lib.wsmg_map_update(P(feat), P(depth), P(gps[t]), P(compass[t]), P(masks[t]), P(gmap), P(ego), None,
                                      P(scratch), scratch.numel(), ctypes.byref(d), sp)
@@ -264,7 +270,7 @@ def run_native(args, rank, local_rank, world):
     for k in range(K):
         if flush_l2:
             flush_buf.fill_(k & 0xFF)
-        step(W + k, kev[k][0], kev[k][1])
+        step(W + K + k, kev[k][0], kev[k][1])      # the walk continues: new frames, new poses
     barrier()
     fused_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
 
@@ -302,7 +308,7 @@ def run_native(args, rank, local_rank, world):
             for k in range(len(ev) + 2):
                 if k >= 2:
                     ev[k - 2][0].record(stream)
-                rc = lib.wsmg_map_update(P(feat), P(dk), P(gps[k]), P(compass[k]), P(masks[k]), P(gmap_d), P(ego), None,
+                rc = lib.wsmg_map_update(P(feat_all[k:k + nd]), P(dk), P(gps[k]), P(compass[k]), P(masks[k]), P(gmap_d), P(ego), None,
                                          P(scratch), scratch.numel(), ctypes.byref(dd_), sp)
                 _lib.check(rc, "wsmg_map_update")
                 if k >= 2:

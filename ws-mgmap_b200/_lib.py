@@ -57,10 +57,11 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("WSMG_LIB_PATH", LIB_PATH)    # override: profiling builds (build.py --phase-skip)
+    if not os.path.exists(path):
         from .build import build_cuda
         build_cuda()
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -37,15 +37,19 @@ def _sources():
     return out
 
 
-def build_cuda(verbose: bool = False, force: bool = False) -> str:
+def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = False) -> str:
+    """phase_skip=True builds the profiling variant lib/libwsmg_phaseskip.so (-DWSMG_PHASE_SKIP, see
+    csrc/wsmg_body.h: WSMG_SKIP); load it with WSMG_LIB_PATH, never in production."""
     os.makedirs(LIB, exist_ok=True)
-    target = os.path.join(LIB, "libwsmg.so")
+    target = os.path.join(LIB, "libwsmg_phaseskip.so" if phase_skip else "libwsmg.so")
     if not force and _newer(target, _sources()):
         return target
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", target, os.path.join(CSRC, "wsmg.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if phase_skip:
+        cmd.insert(1, "-DWSMG_PHASE_SKIP")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
@@ -72,3 +76,5 @@ if __name__ == "__main__":
     v = "-v" in sys.argv
     print(build_cuda(verbose=v, force="-f" in sys.argv))
     print(build_emulation(force="-f" in sys.argv))
+    if "--phase-skip" in sys.argv:
+        print(build_cuda(force=True, phase_skip=True))

@@ -212,6 +212,10 @@ static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
   const int grid = p.bs * ((p.g.C + SLAB - 1) / SLAB);
   const char* force = getenv("WSMG_FORCE_GENERIC");
   const char* no_tma = getenv("WSMG_NO_TMA");
+  p.debug_skip = 0;
+#if defined(WSMG_PHASE_SKIP)
+  if (const char* dbg = getenv("WSMG_DEBUG_SKIP")) p.debug_skip = atoi(dbg);   // profiling build only, see WSMG_SKIP
+#endif
   const bool generic = force && force[0] == '1';
   bool tma = vec && !p.stop_after_scatter && !(no_tma && no_tma[0] == '1');
   if (tma) {

@@ -138,6 +138,7 @@ struct FusedParams {
   float* proj_out;          // optional dump of the pre-rotation grid [bs,C,E,E]
   const float* proj_in;     // optional: take the grid from here instead of scattering
   int stop_after_scatter;   // stage API: return after writing proj_out
+  int debug_skip;           // read only by the -DWSMG_PHASE_SKIP profiling build (scripts/phase_split.py), see WSMG_SKIP
   int bs;
   Geo g;
   SmemPlan sp;
@@ -256,6 +257,15 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
 // TMA: the map window moves through cp.async.bulk.tensor (needs VEC); else cp.async + st.global.
 // POOL: feature channels != map channels, the channel pool of rgb_mapping.py:81-84 runs inside the scatter.
+// Phase-skipping switch of the profiling build (build.py --phase-skip -> lib/libwsmg_phaseskip.so): bit 1 scatter,
+// 2 first rotation, 4 band loop, 8 output rotation, 16 crop, 32 fuse, 64 TMA-arrival wait.  Results are
+// garbage with any bit set; only the timing means something.  The product build compiles it away.
+#if defined(WSMG_PHASE_SKIP)
+#define WSMG_SKIP(bit) ((p.debug_skip & (bit)) != 0)
+#else
+#define WSMG_SKIP(bit) false
+#endif
+
 template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA_BUILD, bool POOL>
 WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, const int tid) {
   const Geo& g = p.g;
@@ -378,7 +388,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   WSMG_SYNC();
 
   // ---- phase 1: scatter-max into the packed fan (rgb_mapping.py:210-225) -----------------------
-  if (p.proj_in == nullptr) {
+  if (p.proj_in == nullptr && !WSMG_SKIP(1)) {
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
     // Channel pool (rgb_mapping.py:81-84) fused: when Cin != C the scatter runs once per input plane of a bin,
     // all passes reducing into the same key plane (max over channels commutes with the max-scatter).
@@ -563,7 +573,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // Cells none of whose taps falls inside the fan (~70 % of the grid) are exact zeros: store and move on.
   // The per-row extent of the other cells lets the fuse step skip window cells that only see zeros.
   const int nslots = tile_slots(E);
-  for (int s0 = 0; s0 < nslots; s0 += NT) {
+  for (int s0 = 0; s0 < (WSMG_SKIP(2) ? 0 : nslots); s0 += NT) {
     const int slot = s0 + tid;
     bool hit = false;
     int i = 0, j = 0;
@@ -683,11 +693,16 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         F4 a = tap(X, rt.a + ct.a), bb = tap(X, rt.a + ct.b), c = tap(X, rt.b + ct.a), d = tap(X, rt.b + ct.b);
         F4 tv = blend_f4(a, bb, c, d, w);
         F4* cellp = ring + cell;
-        F4 f = *cellp;
+        const F4 old = *cellp;
+        F4 f;
+        bool changed = false;
 #pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch) f.v[ch] = fmaxf(f.v[ch], tv.v[ch]);
-        *cellp = f;
-        if (!TMA) {
+        for (int ch = 0; ch < SLAB; ++ch) {
+          f.v[ch] = fmaxf(old.v[ch], tv.v[ch]);
+          changed |= as_int(f.v[ch]) != as_int(old.v[ch]);
+        }
+        if (changed) {             // cells the observation does not raise keep their bytes: no store, no DRAM write
+          *cellp = f;
           float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
           if (VEC) {
             *reinterpret_cast<F4*>(dst) = f;
@@ -712,31 +727,20 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
     p_lo = p_hi;
   };
-  for (int k = 0; k <= NB; ++k) {
+  for (int k = 0; k <= (WSMG_SKIP(4) ? -1 : NB); ++k) {
     if (!TMA && k < NB) {
       if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
     }
     WSMG_SYNC();
     if (TMA) {
-      if (tma_lane >= 0) {
-        if (k >= 1) {              // band k-1 is final in shared memory (fenced + barrier): store it, one row per lane
-          const int kb = k - 1;
-          if (tma_lane < tma_rows(kb)) {
-            const int uu = kb * BAND + tma_lane;
-            tma_store_row(&p.tmap, c0, v0, u0 + uu, mrow, ring + 1 + ((uu + S0) % RR) * WWP);
-          }
-          tma_commit();
-        }
-        if (k + 2 < NB) {
-          tma_wait_read<1>();      // every lane: its stores older than the one just committed have read their rows
-          prefetch_band(k + 2);    // (__syncwarp inside orders all lanes' waits before any load is issued)
-        }
-      }
-      if (k >= 1) crop_rows(k);    // needs only finished F rows: runs while band k is still landing
+      // ring rows of band k+2 were last read by trip k-1's crop (RR >= 4*BAND + 2) and last written by an
+      // earlier fuse (fenced below): the barrier above makes them free for the TMA unit to overwrite
+      if (tma_lane >= 0 && k + 2 < NB) prefetch_band(k + 2);
+      if (k >= 1 && !WSMG_SKIP(16)) crop_rows(k);    // needs only finished F rows: runs while band k is still landing
       if (k < NB) {
-        mbar_wait(&bars[k], 0);
-        fuse_band(k);
-        fence_proxy_async();       // make the fused rows visible to the TMA store issued after the next barrier
+        if (!WSMG_SKIP(64)) mbar_wait(&bars[k], 0);
+        if (!WSMG_SKIP(32)) fuse_band(k);
+        fence_proxy_async();       // generic writes to ring rows precede the TMA load that recycles them
       }
     } else {
       if (k + 2 < NB) prefetch_band(k + 2);
@@ -751,7 +755,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   if (p.trig != nullptr) { cs = p.trig[4 * b + 2]; sn = p.trig[4 * b + 3]; }
   else { float h = p.compass[b]; sn = sinf(h); cs = cosf(h); }
   float* ego_b = p.ego + ((size_t)b * C + c0) * EE;
-  for (int slot = tid; slot < nslots; slot += NT) {
+  for (int slot = tid; slot < (WSMG_SKIP(8) ? 0 : nslots); slot += NT) {
     int i, j;
     if (!tile_cell(slot, E, &i, &j)) continue;
     const int t = i * E + j;
@@ -774,7 +778,6 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         if (ch < nch) half_b[(size_t)ch * EE + t] = f2half_bits(r.v[ch]);
     }
   }
-  if (TMA && tma_lane >= 0) tma_wait_read<0>();   // the last band's stores must have read their rows before the CTA retires
 }
 
 }  // namespace wsmg
