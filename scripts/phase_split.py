@@ -42,7 +42,10 @@ t_dead = timeit(lambda: ops.map_update(feat, dead, gps, compass, ones, gmap, scr
 for mask, name in ((1, "scatter"), (2, "first rotation"), (4, "band loop (incl. its TMA traffic)"), (8, "output rotation"), (15, "all four"),
                    (14, "all but the scatter"), (7, "all but the output rotation"), (16, "band loop: crop (3b) only"),
                    (32, "band loop: fuse (3a) only"), (48, "band loop: crop + fuse, keep TMA + barriers"),
-                   (64, "band loop: the TMA-arrival wait only"), (112, "band loop: crop + fuse + wait (barriers + TMA loads remain)")):
+                   (64, "band loop: the TMA-arrival wait only"), (112, "band loop: crop + fuse + wait (barriers + TMA loads remain)"),
+                   (15 + 512, "all four + key decode"), (15 + 1024, "all four + translation tables"),
+                   (15 + 2048, "all four + key-plane init"), (15 + 512 + 1024 + 2048, "all four + decode + tables + init"),
+                   (4096, "everything: CTAs return at entry (k_reset + k_cells + launch cost)")):
     os.environ["WSMG_DEBUG_SKIP"] = str(mask)
     t = timeit(lambda: ops.map_update(feat, depth, gps, compass, ones, gmap, scratch=scratch, ego=ego))
     print(f"  skip {name:34s} -> {t:.3f} ms  (saves {t_full - t:+.3f})")

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
 // ------------------------------------------------------------------ k_fused
 template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
+  // One CTA per (env, slab).  (A persistent one-CTA-per-SM loop over the items was measured and is not faster:
+  // the hardware already overlaps CTA launch with the previous CTA's tail, and static striding loses balance.)
   extern __shared__ __align__(1024) unsigned char smem[];
   fused_body<FUSED_THREADS, CE, CG, CHW, VEC, TMA, POOL>(p, blockIdx.x, smem, threadIdx.x);
 }

@@ -112,7 +112,7 @@ WSMG_HD SmemPlan make_plan(const Geo& g) {
   s.fanrow_off = s.base_off + align16(g.E * 4);
   s.ext_off = s.fanrow_off + align16((g.E + 2) * 8);         // fanrow[E+1]; after the first rotation the same bytes hold rowE[E+2]
   s.bar_off = s.ext_off + align16(g.E * 8);                  // ext[E]
-  s.total = s.bar_off + MAX_BANDS * 8;
+  s.total = s.bar_off + MAX_BANDS * 8 + 32;                  // + per-CTA scalars (rotation sines / cosines, env flags)
   return s;
 }
 
@@ -258,7 +258,8 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 // TMA: the map window moves through cp.async.bulk.tensor (needs VEC); else cp.async + st.global.
 // POOL: feature channels != map channels, the channel pool of rgb_mapping.py:81-84 runs inside the scatter.
 // Phase-skipping switch of the profiling build (build.py --phase-skip -> lib/libwsmg_phaseskip.so): bit 1 scatter,
-// 2 first rotation, 4 band loop, 8 output rotation, 16 crop, 32 fuse, 64 TMA-arrival wait.  Results are
+// 2 first rotation, 4 band loop, 8 output rotation, 16 crop, 32 fuse, 64 TMA-arrival wait, 512 key decode,
+// 1024 translation tables, 2048 key-plane init, 4096 return at entry (launch cost of an empty CTA).  Results are
 // garbage with any bit set; only the timing means something.  The product build compiles it away.
 #if defined(WSMG_PHASE_SKIP)
 #define WSMG_SKIP(bit) ((p.debug_skip & (bit)) != 0)
@@ -301,6 +302,30 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   I2* rowE = fanrow;                                          // per window row: merged extent of its two source R rows (fanrow is dead by then)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);   // one mbarrier per band (TMA)
   int* chunk_counter = reinterpret_cast<int*>(bars + MAX_BANDS - 1);  // last slot of the barrier array is never a barrier
+  float* scal = reinterpret_cast<float*>(bars + MAX_BANDS);   // {cos, sin}(-compass), {cos, sin}(+compass), env flags
+  if (WSMG_SKIP(4096)) return;
+
+  // ---- per-env scalars that later phases need: fetched and evaluated now by three lanes of three different
+  // warps, parked in shared memory -- their global-memory latency would otherwise stall the whole CTA right
+  // after a barrier (rgb_mapping.py:37,70 -> :239-245)
+  {
+    const int t_r1 = 0, t_r2 = NT > 64 ? 32 : 0, t_fl = NT > 64 ? 64 : 0;
+    if (!p.stop_after_scatter) {
+      if (tid == t_r1) {
+        float cs_, sn_;
+        if (p.trig != nullptr) { cs_ = p.trig[4 * b + 0]; sn_ = p.trig[4 * b + 1]; }
+        else { float h = -p.compass[b]; sn_ = sinf(h); cs_ = cosf(h); }
+        scal[0] = cs_; scal[1] = sn_;
+      }
+      if (tid == t_r2) {
+        float cs_, sn_;
+        if (p.trig != nullptr) { cs_ = p.trig[4 * b + 2]; sn_ = p.trig[4 * b + 3]; }
+        else { float h = p.compass[b]; sn_ = sinf(h); cs_ = cosf(h); }
+        scal[2] = cs_; scal[3] = sn_;
+      }
+    }
+    if (tid == t_fl && p.proj_in == nullptr) scal[4] = as_float((int)p.env_flags[b]);
+  }
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63
   float qx = 0.f, qy = 0.f;
@@ -384,7 +409,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   }
   if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); *chunk_counter = 0; }
   for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
-  for (int t = tid; t < SLAB * npp; t += NT) Pk[t] = KEY_EMPTY;
+  for (int t = tid; t < (WSMG_SKIP(2048) ? 0 : SLAB * npp); t += NT) Pk[t] = KEY_EMPTY;
   WSMG_SYNC();
 
   // ---- phase 1: scatter-max into the packed fan (rgb_mapping.py:210-225) -----------------------
@@ -519,8 +544,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // ---- phase 1b: keys -> finished floats, planar -> F4 per cell (rgb_mapping.py:228-230) -----
   if (p.proj_in == nullptr) {
     const int32_t sentinel_key = f2key(SENTINEL);
-    const bool inv = (p.env_flags[b] & 1u) != 0;
-    for (int t = tid; t < fan_cells; t += NT) {
+    const bool inv = (as_int(scal[4]) & 1) != 0;
+    for (int t = tid; t < (WSMG_SKIP(512) ? 0 : fan_cells); t += NT) {
       F4 v;
 #pragma unroll
       for (int ch = 0; ch < SLAB; ++ch) {
@@ -531,7 +556,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       X[1 + t] = v;
     }
     WSMG_SYNC();
-    for (int t = tid; t < fan_cells; t += NT) Pf[1 + t] = X[1 + t];
+    for (int t = tid; t < (WSMG_SKIP(512) ? 0 : fan_cells); t += NT) Pf[1 + t] = X[1 + t];
   } else {
     // stage API: load the projection (zero outside the fan by construction)
     const float* src = p.proj_in + ((size_t)b * C + c0) * EE;
@@ -567,9 +592,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   if (p.stop_after_scatter) return;
 
   // ---- phase 2: R = rotate(P, -compass) into X (rgb_mapping.py:37 -> :267 -> :239-250) ---------
-  float cs, sn;
-  if (p.trig != nullptr) { cs = p.trig[4 * b + 0]; sn = p.trig[4 * b + 1]; }
-  else { float h = -p.compass[b]; sn = sinf(h); cs = cosf(h); }
+  float cs = scal[0], sn = scal[1];
   // Cells none of whose taps falls inside the fan (~70 % of the grid) are exact zeros: store and move on.
   // The per-row extent of the other cells lets the fuse step skip window cells that only see zeros.
   const int nslots = tile_slots(E);
@@ -626,7 +649,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // rowT[uu] = {1 + y0*E | NEG, 1 + (y0+1)*E | NEG, bits(wy), 1 + slot(uu)*WWP if the row is inside the map else NEG}
   // bXT[q]   = {col0 | NEG, col1 | NEG, bits(wx), 0}
   // bYT[p]   = {1 + slot(row0)*WWP | NEG, 1 + slot(row1)*WWP | NEG, bits(wy), 0}     (slot(r) = (r + S0) % RR)
-  for (int t = tid; t < WW; t += NT) {
+  for (int t = tid; t < (WSMG_SKIP(1024) ? 0 : WW); t += NT) {
     int v = v0 + t, u = u0 + t;
     I4 ct; ct.a = ct.b = NEG; ct.c = 0; ct.d = NEG;
     if ((unsigned)v < (unsigned)G) {    // canvas column sampled by global column v, relative to the pasted ego grid
@@ -656,7 +679,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       rowE[t] = e;
     }
   }
-  for (int t = tid; t < E; t += NT) {   // global column / row sampled by crop cell t, relative to the window
+  for (int t = tid; t < (WSMG_SKIP(1024) ? 0 : E); t += NT) {   // global column / row sampled by crop cell t, relative to the window
     Tap1D tp = make_tap(unnormalize(base_coord(t + paste_lo, G) + qx, half_g));
     int cx = tp.i0 - v0;
     I4 bx; bx.a = (unsigned)cx < (unsigned)WW ? cx : NEG;
@@ -752,8 +775,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   WSMG_SYNC();
 
   // ---- phase 4: ego = rotate(B, +compass), NCHW out (rgb_mapping.py:70) ----------------------
-  if (p.trig != nullptr) { cs = p.trig[4 * b + 2]; sn = p.trig[4 * b + 3]; }
-  else { float h = p.compass[b]; sn = sinf(h); cs = cosf(h); }
+  cs = scal[2]; sn = scal[3];
   float* ego_b = p.ego + ((size_t)b * C + c0) * EE;
   for (int slot = tid; slot < (WSMG_SKIP(8) ? 0 : nslots); slot += NT) {
     int i, j;
