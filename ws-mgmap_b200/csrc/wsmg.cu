@@ -183,7 +183,7 @@ static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const 
   CUtensorMap tm;
   const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.G, (cuuint64_t)g.G, (cuuint64_t)n_maps};
   const cuuint64_t strides[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.G * g.C * 4, (cuuint64_t)g.G * g.G * g.C * 4};
-  const cuuint32_t box[4] = {4, (cuuint32_t)(g.E + 2), 1, 1};
+  const cuuint32_t box[4] = {4, (cuuint32_t)make_plan(g).wwp, (cuuint32_t)TMA_ROWS, 1};   // see prefetch_band
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gmap, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -219,7 +219,7 @@ static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
   if (const char* dbg = getenv("WSMG_DEBUG_SKIP")) p.debug_skip = atoi(dbg);   // profiling build only, see WSMG_SKIP
 #endif
   const bool generic = force && force[0] == '1';
-  bool tma = vec && !p.stop_after_scatter && !(no_tma && no_tma[0] == '1');
+  bool tma = vec && !p.stop_after_scatter && !(no_tma && no_tma[0] == '1') && p.sp.wwp <= p.g.G;   // box no wider than the map
   if (tma) {
     int rc = encode_window_map(&p.tmap, p.gmap, n_maps, p.g);
     if (rc != 0) return rc;

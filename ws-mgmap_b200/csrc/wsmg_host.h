@@ -19,7 +19,7 @@ inline int validate_dims(const wsmg_dims* d) {
   if (d->n_maps < d->bs) return WSMG_E_BATCH;
   if (d->C_in < 0) return WSMG_E_CHANNELS;
   if ((d->Hf * d->Wf) % 4 != 0) return WSMG_E_ALIGN;
-  if (d->E > 126 || d->G > 32768) return WSMG_E_DIMS;          // 16-bit fan codes; (E+2)/9 bands must fit the barrier array
+  if (d->E > 126 || d->G > 32768) return WSMG_E_DIMS;          // 16-bit fan codes; (E+2)/8 bands must fit the barrier array
   return WSMG_OK;
 }
 
