@@ -19,6 +19,7 @@ if [ "$MODE" = "full" ]; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 4 -c 2 -f -o $OUT/prof_fused \
       python bench.py --envs 256 --steps 4 --warmup 3 --no-cpu-baseline --e2e-envs 16 --e2e-steps 2 --no-by-depth > $OUT/ncu_full.log 2>&1
   ls -la $OUT/*.ncu-rep
+  [ -f ws-mgmap_b200/lib/libwsmg_phaseskip.so ] && { echo "== phase split"; timeout 600 python scripts/phase_split.py > $OUT/phase_split.txt 2>&1; tail -3 $OUT/phase_split.txt; }
   echo "== racecheck (small)"
   timeout 600 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -q -x -k golden_trajectory 2>&1 | tail -8 | tee $OUT/racecheck.log
 fi

@@ -29,8 +29,9 @@ with open(f"profiles/{tag}_k_fused_ncu_full.txt", "w") as f:
                 i = hdr.index(k)
                 f.write(f"{k:78s} {r[i]:>18s} {units[i]}\n")
         rd = float(r[hdr.index('dram__bytes_read.sum')]); wr = float(r[hdr.index('dram__bytes_write.sum')])
-        un = units[hdr.index('dram__bytes_read.sum')]
-        mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[un]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+        rd *= scale[units[hdr.index('dram__bytes_read.sum')]]; wr *= scale[units[hdr.index('dram__bytes_write.sum')]]
+        mult = 1
         if li == 0:
             json.dump({"k_fused_dram_bytes_per_env": (rd + wr) * mult / 256, "source": f"profiles/{tag}_k_fused_ncu_full.txt",
                        "how": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one k_fused launch over 256 envs"},
@@ -46,3 +47,4 @@ cp gpurun_out/bench_env8.json $OUT/${TAG}_bench_env8.json 2>/dev/null
 cp gpurun_out/microbench_atoms.log $OUT/${TAG}_microbench_atoms.txt 2>/dev/null
 cp gpurun_out/racecheck.log $OUT/${TAG}_racecheck.txt 2>/dev/null
 ls -la $OUT | tail -12
+cp gpurun_out/phase_split.txt $OUT/${TAG}_phase_split.txt 2>/dev/null

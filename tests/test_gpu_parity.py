@@ -278,3 +278,34 @@ def test_edge_frames_match_oracle():
                              trig=_trig(compass).to(DEV))
         assert torch.equal(ego.cpu(), want), name
         assert torch.equal(gmap.cpu(), orc.full_global_map), name
+
+
+def test_window_touching_the_map_border():
+    """Windows whose last row / column is exactly the map's last one (the TMA boxes then reach past the tensor and
+    are zero-filled there), one cell inside, and one cell outside (clipped: cp.async path) -- all bit-identical to
+    the oracle; and a repeated identical frame changes no byte of the map (max-fusion is idempotent, the kernel
+    then stores nothing)."""
+    c, hf, hd = 64, 224, 256
+    # gps -> window origin: u0 = 51 - 1 + round((14.4 - gps0)/0.12) - 120 ... u0 = 138 <=> gps0 = -8.28, u0 = 0 <=> gps0 = 8.28
+    g0 = [8.28, 8.16, -8.28, -8.16, -8.40, 8.40, 0.0, -8.28]
+    g1 = [-8.28, 8.28, 8.28, -8.16, 8.40, 0.0, -8.40, -8.28]
+    bs = len(g0)
+    gen = torch.Generator().manual_seed(77)
+    gps = torch.tensor(list(zip(g0, g1)), dtype=torch.float32)
+    compass = torch.rand(bs, 1, generator=gen) * 6 - 3
+    orc = OracleMapper(bs, c)
+    orc.full_global_map += 0.125
+    gmap = orc.full_global_map.clone().to(DEV)
+    ones = torch.ones(bs, 1)
+    for t in range(2):
+        feat = make_features(bs, c, hf, hf, gen)
+        depth = make_depth(("room4", "near")[t], bs, hd, hd, gen)
+        want = orc.step(feat, depth, gps, compass, ones, keep=True)
+        ego = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), ones.to(DEV), gmap,
+                             trig=_trig(compass).to(DEV))
+        assert torch.equal(ego.cpu(), want), t
+        assert torch.equal(gmap.cpu(), orc.full_global_map), t
+    before = gmap.clone()
+    ego2 = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), ones.to(DEV), gmap,
+                          trig=_trig(compass).to(DEV))
+    assert torch.equal(gmap, before) and torch.equal(ego2.cpu(), want)
