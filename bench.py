@@ -277,7 +277,7 @@ def run_native(args, rank, local_rank, world):
     # ---- end to end from pinned host buffers (`e2e`) ----------------------------------------
     ne = min(n, args.e2e_envs)
     de = ops.dims_for((ne,) + tuple(feat.shape[1:]), depth[:ne].shape, ne, s["E"], s["G"], s["resolution"])
-    pipe = ops.HostPipeline(de, dev, chunk_envs=args.e2e_chunk)
+    pipe = ops.HostPipeline(de, dev, chunk_envs=args.e2e_chunk, zero_copy=args.e2e_mode == "zerocopy")
     feat_h = feat[:ne].cpu().pin_memory()
     depth_h = depth[:ne].cpu().pin_memory()
     gps_h, comp_h, mask_h = (x[:, :ne].contiguous().cpu().pin_memory() for x in (gps, compass, masks))
@@ -394,6 +394,8 @@ def main():
     ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU in the host-buffer (e2e) leg")
     ap.add_argument("--e2e-chunk", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-mode", default="copy", choices=["copy", "zerocopy"],
+                    help="host-buffer leg: stage the features with cudaMemcpyAsync, or let the scatter read the pinned buffer")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per k_fused launch from ncu, if known")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-by-depth", action="store_true", help="skip the per-depth-distribution runs")

@@ -35,7 +35,8 @@ enum {
   WSMG_E_SMEM = -5,        /* geometry needs more shared memory than one SM has   */
   WSMG_E_ALIGN = -6,       /* pointer not 16-byte aligned / Hf*Wf not multiple of 4 */
   WSMG_E_SCRATCH = -7,     /* scratch buffer too small                            */
-  WSMG_E_BATCH = -8        /* bs larger than the map tensor's leading dimension   */
+  WSMG_E_BATCH = -8,       /* bs larger than the map tensor's leading dimension   */
+  WSMG_E_HOSTMEM = -9      /* zero-copy asked for, but the host buffer is not device-mapped pinned memory */
 };
 
 /* Geometry of one call.  Mirrors Mapping.__init__ (rgb_mapping.py:12-30) and the
@@ -149,6 +150,17 @@ int wsmg_map_update_host(const float* feat_host, const float* depth_host, const 
                          const float* compass_host, const float* mask_host, float* gmap,
                          float* ego_out_host, void* staging, size_t staging_bytes,
                          int32_t chunk_envs, const wsmg_dims* d, void* stream);
+
+
+/* wsmg_map_update_host with options.  WSMG_HOST_ZEROCOPY_FEATURES: `feat_host` must be page-locked, device-mapped
+ * host memory (cudaHostAlloc / cudaHostRegister, torch `pin_memory()`); the scatter then pulls the features over
+ * the bus itself and the 4-pixel groups that cannot write (typically 45-50 % of a frame) never cross it.  Replaces
+ * the H2D half of batch_obs (common_trainer / dagger_trainer) for the feature tensor.  Everything else as above. */
+enum { WSMG_HOST_ZEROCOPY_FEATURES = 1 };
+int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, const float* gps_host,
+                            const float* compass_host, const float* mask_host, float* gmap,
+                            float* ego_out_host, void* staging, size_t staging_bytes,
+                            int32_t chunk_envs, const wsmg_dims* d, uint32_t flags, void* stream);
 
 #ifdef __cplusplus
 }

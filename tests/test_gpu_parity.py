@@ -172,6 +172,16 @@ def test_stage_composition_and_host_pipeline():
     pipe.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g3, ego_h)
     torch.cuda.synchronize()
     assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g3, g2)
+    # zero-copy features: the scatter reads the pinned host tensor itself; pageable memory is refused
+    pipe0 = ops.HostPipeline(d, DEV, chunk_envs=3, zero_copy=True)
+    g4 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego_h.zero_()
+    pipe0.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)
+    torch.cuda.synchronize()
+    assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g4, g2)
+    from wsmgmap_b200._lib import WsmgError
+    with pytest.raises(WsmgError):
+        pipe0.step(feat.clone(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)
 
 
 def test_full_size_properties():

@@ -40,12 +40,17 @@ SIGNATURES = {
     "wsmg_base_coords_host": (ctypes.c_int, [_P, ctypes.c_int32]),
     "wsmg_host_staging_bytes": (ctypes.c_size_t, [_DP, ctypes.c_int32]),
     "wsmg_map_update_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP, _P]),
+    "wsmg_map_update_host_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP,
+                                               ctypes.c_uint32, _P]),
 }
 
 FLAG_INVALID_PIXEL = 1
 FLAG_OUTSIDE_FAN = 2
 
 _lib = None
+
+
+HOST_ZEROCOPY_FEATURES = 1   # include/wsmg.h: WSMG_HOST_ZEROCOPY_FEATURES
 
 
 class WsmgError(RuntimeError):

@@ -399,6 +399,14 @@ size_t wsmg_host_staging_bytes(const wsmg_dims* d, int32_t chunk_envs) {
 int wsmg_map_update_host(const float* feat_host, const float* depth_host, const float* gps_host,
                          const float* compass_host, const float* mask_host, float* gmap, float* ego_out_host,
                          void* staging, size_t staging_bytes, int32_t chunk_envs, const wsmg_dims* d, void* stream) {
+  return wsmg_map_update_host_ex(feat_host, depth_host, gps_host, compass_host, mask_host, gmap, ego_out_host, staging,
+                                 staging_bytes, chunk_envs, d, 0u, stream);
+}
+
+int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, const float* gps_host,
+                            const float* compass_host, const float* mask_host, float* gmap, float* ego_out_host,
+                            void* staging, size_t staging_bytes, int32_t chunk_envs, const wsmg_dims* d, uint32_t flags,
+                            void* stream) {
   int rc = validate_dims(d);
   if (rc != WSMG_OK) return rc;
   if (!feat_host || !depth_host || !gps_host || !compass_host || !mask_host || !gmap || !ego_out_host || !staging)
@@ -406,6 +414,17 @@ int wsmg_map_update_host(const float* feat_host, const float* depth_host, const 
   if (chunk_envs <= 0) return WSMG_E_DIMS;
   const int chunk = chunk_envs < d->bs ? chunk_envs : d->bs;
   if (staging_bytes < wsmg_host_staging_bytes(d, chunk) || !aligned16(staging)) return WSMG_E_SCRATCH;
+  // zero-copy: the kernel reads the caller's pinned buffer through its device mapping
+  const float* feat_mapped = nullptr;
+  if (flags & WSMG_HOST_ZEROCOPY_FEATURES) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, feat_host) != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) {
+      cudaGetLastError();
+      return WSMG_E_HOSTMEM;
+    }
+    feat_mapped = static_cast<const float*>(at.devicePointer);
+    if (!aligned16(feat_mapped)) return WSMG_E_ALIGN;
+  }
   cudaStream_t user = (cudaStream_t)stream;
   // two internal streams ping-pong over the two staging slots so that the copies of chunk i+1
   // overlap the kernels of chunk i; both are fenced against the caller's stream with events.
@@ -429,13 +448,13 @@ int wsmg_map_update_host(const float* feat_host, const float* depth_host, const 
     slot_bytes(d, chunk, &hs, (unsigned char*)staging + slot * one);
     cudaStream_t s = st[slot];
     const size_t fe = (size_t)(d->C_in > 0 ? d->C_in : d->C) * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
-    cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
+    if (feat_mapped == nullptr) cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.compass, compass_host + b0, n * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.mask, mask_host + b0, n * 4, cudaMemcpyHostToDevice, s);
     wsmg_dims dc = *d; dc.bs = n; dc.n_maps = n;
-    rc = wsmg_map_update(hs.feat, hs.depth, hs.gps, hs.compass, hs.mask, gmap + b0 * per_map, hs.ego, nullptr,
+    rc = wsmg_map_update(feat_mapped != nullptr ? feat_mapped + b0 * fe : hs.feat, hs.depth, hs.gps, hs.compass, hs.mask, gmap + b0 * per_map, hs.ego, nullptr,
                          hs.scratch, hs.scratch_bytes, &dc, s);
     if (rc == 0) cudaMemcpyAsync(ego_out_host + b0 * ee, hs.ego, n * ee * 4, cudaMemcpyDeviceToHost, s);
   }

@@ -62,6 +62,7 @@ inline const char* error_string(int code) {
     case WSMG_E_ALIGN: return "pointer not 16-byte aligned or Hf*Wf not a multiple of 4";
     case WSMG_E_SCRATCH: return "scratch buffer too small";
     case WSMG_E_BATCH: return "bs larger than the map tensor's leading dimension";
+    case WSMG_E_HOSTMEM: return "zero-copy needs page-locked, device-mapped host memory";
     default: return nullptr;
   }
 }

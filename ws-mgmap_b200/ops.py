@@ -110,9 +110,11 @@ def register_fuse_retrieve(proj, gps, compass, mask, gmap, resolution=0.12, trig
 
 class HostPipeline:
     """End-to-end step from HOST (pinned) buffers: H2D of the frame, update, D2H of the ego map,
-    chunked so copies overlap the kernels (wsmg_map_update_host)."""
+    chunked so copies overlap the kernels (wsmg_map_update_host_ex).  zero_copy=True: the feature tensor must be
+    pinned (`pin_memory()`); the scatter pulls it over the bus itself and skips the pixel groups that cannot write."""
 
-    def __init__(self, dims, device, chunk_envs=32):
+    def __init__(self, dims, device, chunk_envs=32, zero_copy=False):
+        self.flags = _lib.HOST_ZEROCOPY_FEATURES if zero_copy else 0
         self.lib = _lib.load()
         self.dims = dims
         self.device = torch.device(device)
@@ -124,7 +126,7 @@ class HostPipeline:
 
     def step(self, feat_h, depth_h, gps_h, compass_h, mask_h, gmap, ego_h):
         with torch.cuda.device(self.device):
-            rc = self.lib.wsmg_map_update_host(_ptr(feat_h), _ptr(depth_h), _ptr(gps_h), _ptr(compass_h), _ptr(mask_h),
-                                               _ptr(gmap), _ptr(ego_h), _ptr(self.staging), self.staging.numel(),
-                                               self.chunk, ctypes.byref(self.dims), _stream(self.device))
-        _lib.check(rc, "wsmg_map_update_host")
+            rc = self.lib.wsmg_map_update_host_ex(_ptr(feat_h), _ptr(depth_h), _ptr(gps_h), _ptr(compass_h), _ptr(mask_h),
+                                                  _ptr(gmap), _ptr(ego_h), _ptr(self.staging), self.staging.numel(),
+                                                  self.chunk, ctypes.byref(self.dims), self.flags, _stream(self.device))
+        _lib.check(rc, "wsmg_map_update_host_ex")
