@@ -336,9 +336,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     v0 = (int)sx + paste_lo - 1;
     gmap_b = p.gmap + (size_t)mrow * G * G * C + c0;
   }
-  // TMA stores must not leave the tensor: a window clipped by the map border (agent within ~6 m of the
-  // edge of the 28.8 m map) takes the cp.async / st.global path instead.  CTA-uniform.
-  const bool TMA = TMA_BUILD && u0 >= 0 && v0 >= 0 && u0 + WW <= G && v0 + WW <= G;
+  // The window is only ever LOADED through TMA, and a tiled load zero-fills whatever lies outside the tensor
+  // (negative coordinates included): windows clipped by the map border need no special path.
+  constexpr bool TMA = TMA_BUILD;
 
   // Band k of the caller's map window -> its ring rows; cells outside the map arrive as zeros.
   // TMA: boxes of TMA_ROWS x WWP cells, issued by the first lanes of the last warp (it owns no window / crop
