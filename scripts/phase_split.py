@@ -45,6 +45,8 @@ for mask, name in ((1, "scatter"), (2, "first rotation"), (4, "band loop (incl. 
                    (64, "band loop: the TMA-arrival wait only"), (112, "band loop: crop + fuse + wait (barriers + TMA loads remain)"),
                    (15 + 512, "all four + key decode"), (15 + 1024, "all four + translation tables"),
                    (15 + 2048, "all four + key-plane init"), (15 + 512 + 1024 + 2048, "all four + decode + tables + init"),
+                   (16384, "scatter: the shared-memory atomics only"), (32768, "scatter: the feature copies only (cp.async)"),
+                   (16384 + 32768, "scatter: atomics + copies (codes, staging reads, run merging remain)"),
                    (4096, "everything: CTAs return at entry (k_reset + k_cells + launch cost)")):
     os.environ["WSMG_DEBUG_SKIP"] = str(mask)
     t = timeit(lambda: ops.map_update(feat, depth, gps, compass, ones, gmap, scratch=scratch, ego=ego))

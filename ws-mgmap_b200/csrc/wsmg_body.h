@@ -150,6 +150,8 @@ struct FusedParams {
 // ------------------------------------------------------------------ platform shims
 #if defined(__CUDACC__)
 __device__ __forceinline__ void smem_max(int32_t* a, int32_t v) { atomicMax(a, v); }
+// true when no active lane of the (converged) warp has the sign bit set in `bits`
+__device__ __forceinline__ bool warp_all_nonneg(int32_t bits) { return __ballot_sync(__activemask(), bits < 0) == 0u; }
 __device__ __forceinline__ F4 ld_stream4(const float* p) {
   float4 t = __ldcs(reinterpret_cast<const float4*>(p));
   F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
@@ -194,6 +196,7 @@ __device__ __forceinline__ void tma_load_box(void* dst, const void* tmap, int c,
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 #else
 inline void smem_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
+inline bool warp_all_nonneg(int32_t bits) { return bits >= 0; }
 inline F4 ld_stream4(const float* p) { F4 r; for (int i = 0; i < 4; ++i) r.v[i] = p[i]; return r; }
 inline uint2 ld_codes(const uint2* p) { return *p; }
 inline void st_stream(float* p, float v) { *p = v; }
@@ -251,7 +254,8 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
 // POOL: feature channels != map channels, the channel pool of rgb_mapping.py:81-84 runs inside the scatter.
 // Phase-skipping switch of the profiling build (build.py --phase-skip -> lib/libwsmg_phaseskip.so): bit 1 scatter,
 // 2 first rotation, 4 band loop, 8 output rotation, 16 crop, 32 fuse, 64 TMA-arrival wait, 512 key decode,
-// 1024 translation tables, 2048 key-plane init, 4096 return at entry (launch cost of an empty CTA).  Results are
+// 1024 translation tables, 2048 key-plane init, 4096 return at entry (launch cost of an empty CTA),
+// 16384 the scatter's shared-memory atomics, 32768 the scatter's feature copies.  Results are
 // garbage with any bit set; only the timing means something.  The product build compiles it away.
 #if defined(WSMG_PHASE_SKIP)
 #define WSMG_SKIP(bit) ((p.debug_skip & (bit)) != 0)
@@ -293,7 +297,6 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   I2* ext = reinterpret_cast<I2*>(smem + sp.ext_off);         // per R row: [first, last] column with a tap inside the fan
   I2* rowE = fanrow;                                          // per window row: merged extent of its two source R rows (fanrow is dead by then)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);   // one mbarrier per band (TMA)
-  int* chunk_counter = reinterpret_cast<int*>(bars + MAX_BANDS - 1);  // last slot of the barrier array is never a barrier
   float* scal = reinterpret_cast<float*>(bars + MAX_BANDS);   // {cos, sin}(-compass), {cos, sin}(+compass), env flags
   if (WSMG_SKIP(4096)) return;
 
@@ -401,7 +404,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
     fanrow[t] = fr;
   }
-  if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); *chunk_counter = 0; }
+  if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); }
   for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
   for (int t = tid; t < (WSMG_SKIP(2048) ? 0 : SLAB * npp); t += NT) Pk[t] = KEY_EMPTY;
   WSMG_SYNC();
@@ -427,11 +430,6 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     size_t plane_off[SLAB];                                   // element offset of this pass's input plane per output channel
 #pragma unroll
     for (int ch = 0; ch < SLAB; ++ch) plane_off[ch] = (size_t)(bin_lo[ch] + (pass < bin_n[ch] ? pass : bin_n[ch] - 1)) * HW;
-    if (pass > 0) {                                           // all warps done with the previous pass: restart the chunk counter
-      WSMG_SYNC();
-      if (tid == 0) *chunk_counter = 0;
-      WSMG_SYNC();
-    }
     // Feature staging through shared memory: X is idle until phase 2, so every thread owns STAGES private
     // 64-byte slots in it ([slot][channel][thread] float4s: conflict-free) and keeps STAGES groups (4 pixels x 4
     // channels) in flight with cp.async while it reduces the oldest one -- no registers are tied up by loads in
@@ -450,39 +448,27 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       return c;
     };
     auto is_live = [](uint2 c) { return ((c.x & c.y) | 0x00010001u) != 0xFFFFFFFFu; };   // (codes past the end are 0xFFFF)
+    const float* feat_slab = feat_b + (size_t)c0 * HW;        // plane of the slab's first channel (no pool)
     auto issue = [&](int slot, int tt, uint2 c) {
       if (is_live(c)) {
-        const float* src = feat_b + 4 * (size_t)tt;
+        const float* src = (pool ? feat_b : feat_slab) + 4 * (size_t)tt;
+        F4* dst = stage + slot * SLAB * NT + tid;
 #pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch)
-          if (ch < nch) async_copy16(stage + (slot * SLAB + ch) * NT + tid, src + (pool ? plane_off[ch] : (size_t)(c0 + ch) * HW), true);
+        for (int ch = 0; ch < SLAB; ++ch)   // without the pool the four planes are compile-time offsets of one pointer
+          if (ch < nch && !WSMG_SKIP(32768)) async_copy16(dst + ch * NT, src + (pool ? plane_off[ch] : (size_t)ch * HW), true);
       }
       async_commit();                                          // one group per step, live or not: wait counts stay exact
     };
-    // Work distribution: warps pull chunks of 32 consecutive groups from a shared counter (dynamic, so that all
-    // warps reach the barrier together however the valid pixels are distributed); a thread's group in chunk c is
-    // c*CH + lane.  tq[] holds the group indices of the steps in flight.
-    constexpr int CH = NT >= 32 ? 32 : NT;
-    const int lane_c = tid % CH;
-    auto next_group = [&]() -> int {
-      int c = 0;
-#if defined(__CUDACC__)
-      if (lane_c == 0) c = atomicAdd(chunk_counter, 1);
-      c = __shfl_sync(0xFFFFFFFFu, c, 0);
-#else
-      c = (*chunk_counter)++;
-#endif
-      return c * CH + lane_c;
-    };
-    int tq[QD];
+    // Work distribution: warp w takes the chunks of 32 consecutive groups w, w + warps, w + 2*warps, ... (a thread's
+    // group in chunk c is c*32 + lane), which samples every image row band evenly.  (Pulling chunks from a shared counter was measured at 1, 2, 4 and 8 chunks per pull:
+    // 1.5-4.5 % slower than this static striding.)
+    // With NT a multiple of 32 that is simply: the thread's k-th group is tid + k*NT.
+    int t_head = tid;                                          // group index of cq[0]; cq[s] belongs to t_head + s*NT
 #pragma unroll
-    for (int s_ = 0; s_ < QD; ++s_) {
-      tq[s_] = next_group();
-      cq[s_] = fetch_codes(tq[s_]);
-    }
+    for (int s_ = 0; s_ < QD; ++s_) cq[s_] = fetch_codes(t_head + s_ * NT);
 #pragma unroll
-    for (int s_ = 0; s_ < STAGES; ++s_) issue(s_, tq[s_], cq[s_]);
-    for (int it = 0; tq[0] - lane_c < n4; ++it) {             // warp-uniform: chunk start < n4
+    for (int s_ = 0; s_ < STAGES; ++s_) issue(s_, t_head + s_ * NT, cq[s_]);
+    for (int it = 0; t_head - (tid % 32) < n4; ++it) {        // warp-uniform: the warp's first lane still has a group
       const int slot = it % STAGES;
       const uint2 cc = cq[0];
       async_wait<STAGES - 1>();                                // this group's copies have landed
@@ -502,34 +488,35 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch)
           if (ch < nch) sign |= f_bits(f[ch].v[0]) | f_bits(f[ch].v[1]) | f_bits(f[ch].v[2]) | f_bits(f[ch].v[3]);
-        const bool nonneg = sign >= 0;
-        float run[SLAB];
+        // warp-uniform, so the common case (every lane non-negative) carries no key conversion at all
+        const bool nonneg = warp_all_nonneg(sign);
+        auto reduce_group = [&](auto to_key) {
 #pragma unroll
-        for (int px = 0; px < 4; ++px) {
-          const bool same = px > 0 && code[px] == code[px - 1];
+          for (int px = 0; px < 4; ++px) {
+            if (px > 0 && code[px] == code[px - 1]) {           // running max of the run, in place (predicated FMNMX)
 #pragma unroll
-          for (int ch = 0; ch < SLAB; ++ch) {
-            float m = f[ch].v[px];
-            if (same) m = fmaxf(run[ch], m);
-            run[ch] = m;
+              for (int ch = 0; ch < SLAB; ++ch) f[ch].v[px] = fmaxf(f[ch].v[px - 1], f[ch].v[px]);
+            }
+            // ptxas turns a predicated shared atomic into its own branch region, so one branch per pixel (the
+            // predicate is shared by the four channel planes) is the cheapest form
+            if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
+              int32_t* cell = Pk + code[px];
+#pragma unroll
+              for (int ch = 0; ch < SLAB; ++ch)
+                if (ch < nch && !WSMG_SKIP(16384)) smem_max(cell + ch * npp, to_key(f[ch].v[px]));
+            }
           }
-          // ptxas turns a predicated shared atomic into its own branch region, so one branch per pixel (the
-          // predicate is shared by the four channel planes) is the cheapest form
-          if (code[px] < CODE_OUTLIER && code[px] != code[px + 1]) {
-            int32_t* cell = Pk + code[px];
-#pragma unroll
-            for (int ch = 0; ch < SLAB; ++ch)
-              if (ch < nch) smem_max(cell + ch * npp, nonneg ? f_bits(run[ch]) : f2key(run[ch]));
-          }
-        }
+        };
+        if (nonneg) reduce_group([](float v) { return f_bits(v); });
+        else reduce_group([](float v) { return f2key(v); });
       }
       // refill the slot just consumed with the group STAGES steps ahead; advance the queues.  (Refilling before
       // the reduction, with the values already in registers, was measured: 2.5 % slower.)
 #pragma unroll
-      for (int s_ = 0; s_ + 1 < QD; ++s_) { cq[s_] = cq[s_ + 1]; tq[s_] = tq[s_ + 1]; }
-      issue(slot, tq[STAGES - 1], cq[STAGES - 1]);
-      tq[QD - 1] = next_group();
-      cq[QD - 1] = fetch_codes(tq[QD - 1]);
+      for (int s_ = 0; s_ + 1 < QD; ++s_) cq[s_] = cq[s_ + 1];
+      t_head += NT;
+      issue(slot, t_head + (STAGES - 1) * NT, cq[STAGES - 1]);
+      cq[QD - 1] = fetch_codes(t_head + (QD - 1) * NT);
     }
     async_wait<0>();
     }   // pass
