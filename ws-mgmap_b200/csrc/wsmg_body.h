@@ -468,6 +468,11 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     for (int s_ = 0; s_ < QD; ++s_) cq[s_] = fetch_codes(t_head + s_ * NT);
 #pragma unroll
     for (int s_ = 0; s_ < STAGES; ++s_) issue(s_, t_head + s_ * NT, cq[s_]);
+    // unrolled by lcm(QD, STAGES): the code queue's rotation and the slot index turn into register renaming and
+    // immediates (measured: -3 % kernel time over the rolled loop; unroll 2 or a shorter / longer queue are slower)
+    constexpr int UNR = QD * STAGES;
+    static_assert(QD % STAGES != 0, "unroll factor assumes coprime queue depth and stage count");
+#pragma unroll UNR
     for (int it = 0; t_head - (tid % 32) < n4; ++it) {        // warp-uniform: the warp's first lane still has a group
       const int slot = it % STAGES;
       const uint2 cc = cq[0];
