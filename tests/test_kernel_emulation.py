@@ -206,3 +206,38 @@ def test_fused_channel_pool(c_in, c_out):
                           trig=_trig(compass), want_proj=True, map_depth=c_out)
     assert np.array_equal(proj, orc.last["proj"].numpy())
     assert np.array_equal(ego, want.numpy()) and np.array_equal(gmap, orc.full_global_map.numpy())
+
+
+@pytest.mark.parametrize("e,gl", [(100, 240), (61, 150), (30, 64)])
+def test_first_rotation_column_bounds_cut_nothing(e, gl):
+    """The kernel skips the cells of the first rotation that cannot see the fan (per-row column bounds).  With
+    EVERY fan cell occupied, any cell it wrongly skipped would come out 0 instead of > 0: sweep headings
+    (multiples of 15 and 45 degrees, +-pi, tiny angles, random ones) against the elementwise spec."""
+    from oracle.mapping_oracle import spec_rotate, spec_translate, spec_gps_cell
+    geo = MapGeometry(resolution=0.12, ego=e, glob=gl)
+    rng = np.random.default_rng(e)
+    proj = np.zeros((1, 4, e, e), np.float32)
+    for y in range(e // 2 + 1):                      # the whole packed fan (csrc/wsmg_math.h: fan_x_lo / fan_x_hi)
+        proj[0, :, y, max(y - 2, 0):min(e - y + 1, e - 1) + 1] = rng.uniform(0.5, 1.0, size=(4, 1)).astype(np.float32)
+    angles = [k * np.pi / 12 for k in range(-12, 13)] + [1e-7, -1e-7, 1e-3, np.pi - 1e-6, -np.pi + 1e-6]
+    angles += list(rng.uniform(-np.pi, np.pi, 40))
+    lo, hi = geo.paste_lo, geo.paste_hi
+    for a in angles:
+        compass = np.array([[a]], np.float32)
+        gps = rng.uniform(-1.0, 1.0, size=(1, 2)).astype(np.float32)
+        trig = _trig(torch.from_numpy(compass))
+        gmap = np.zeros((1, gl, gl, 4), np.float32)
+        ego, _ = emul_step(gmap, None, None, gps, compass, np.zeros((1, 1), np.float32), trig=trig, mode=2, proj_in=proj,
+                           e=e, g=gl)
+        t = _trig_dict(trig)
+        rot = spec_rotate(proj[0], t["neg"][0][0], t["neg"][1][0])
+        canvas = np.zeros((4, gl, gl), np.float32)
+        canvas[:, lo:hi, lo:hi] = rot
+        gxc, gyc = spec_gps_cell(gps, geo)
+        half = np.float32(gl // 2)
+        tx = -(((gyc[0] - half).astype(np.float32)) / half).astype(np.float32)
+        ty = -(((gxc[0] - half).astype(np.float32)) / half).astype(np.float32)
+        fused = np.maximum(0, spec_translate(canvas, tx, ty).transpose(1, 2, 0))
+        assert np.array_equal(gmap[0], fused), a
+        back = spec_translate(np.ascontiguousarray(fused.transpose(2, 0, 1)), -tx, -ty)
+        assert np.array_equal(ego[0], spec_rotate(back[:, lo:hi, lo:hi], t["pos"][0][0], t["pos"][1][0])), a

@@ -24,9 +24,16 @@ constexpr int CELLS_THREADS = 256;
 // full_global_map[:bs] *= masks (rgb_mapping.py:35).  mask == 1 (the steady state) touches nothing.
 __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
                                                size_t per_env, uint32_t* __restrict__ env_flags,
-                                               const int32_t* __restrict__ env_slots) {
+                                               const int32_t* __restrict__ env_slots, int32_t* __restrict__ row_bounds,
+                                               const float* __restrict__ compass, const float* __restrict__ trig, Geo g) {
   const int b = blockIdx.y;
   if (env_flags != nullptr && blockIdx.x == 0 && threadIdx.x == 0) env_flags[b] = 0u;   // k_cells (next launch) sets them
+  if (row_bounds != nullptr && blockIdx.x == gridDim.x - 1) {     // per-env column bounds of the first rotation (wsmg_body.h)
+    float cs, sn;
+    if (trig != nullptr) { cs = trig[4 * b + 0]; sn = trig[4 * b + 1]; }
+    else { const float h = -compass[b]; sn = sinf(h); cs = cosf(h); }
+    for (int t = threadIdx.x; t < g.E; t += blockDim.x) row_bounds[(size_t)b * g.E + t] = rot_row_bounds(g, cs, sn, t);
+  }
   if (gmap == nullptr) return;
   const float m = mask[b];
   if (m == 1.0f) return;
@@ -142,10 +149,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const int32_t* env_slots, const wsmg_dims* d,
-                        cudaStream_t s) {
+                        cudaStream_t s, int32_t* row_bounds = nullptr, const float* compass = nullptr,
+                        const float* trig = nullptr) {
   const size_t per_env = (size_t)d->G * d->G * d->C;
   dim3 grid(gmap ? 16 : 1, d->bs);
-  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags, env_slots);
+  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags, env_slots, row_bounds, compass, trig, make_geo(d));
   return (int)cudaGetLastError();
 }
 
@@ -284,11 +292,13 @@ static int map_update_impl(const float* feat, const float* depth, const float* g
   const Geo g = make_geo(d);
   uint16_t* codes = (uint16_t*)scratch;
   uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
-  rc = launch_reset(gmap, mask, flags, env_slots, d, s);
+  int32_t* bounds = (int32_t*)((unsigned char*)flags + scratch_flags_bytes(d));
+  rc = launch_reset(gmap, mask, flags, env_slots, d, s, bounds, compass, trig);
   if (rc) return rc;
   rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
+  p.row_bounds = bounds;
   p.feat = feat; p.codes = codes; p.env_flags = flags; p.gps = gps; p.compass = compass; p.trig = trig;
   p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
   p.ego_half = (uint16_t*)ego_half; p.env_slots = env_slots;

@@ -115,7 +115,8 @@ WSMG_HD SmemPlan make_plan(const Geo& g) {
   s.fanrow_off = s.base_off + align16(g.E * 4);
   s.ext_off = s.fanrow_off + align16((g.E + 2) * 8);         // fanrow[E+1]; after the first rotation the same bytes hold rowE[E+2]
   s.bar_off = s.ext_off + align16(g.E * 8);                  // ext[E]
-  s.total = s.bar_off + MAX_BANDS * 8 + 32;                  // + per-CTA scalars (rotation sines / cosines, env flags)
+  s.total = s.bar_off + MAX_BANDS * 8 + 32 + align16(g.E * 4);   // + per-CTA scalars (rotation sines / cosines, env flags)
+                                                                  // + per-row column bounds of the first rotation
   return s;
 }
 
@@ -138,6 +139,7 @@ struct FusedParams {
   float* ego;               // [bs,C,E,E]
   uint16_t* ego_half;       // optional [bs,C,E,E] IEEE binary16 copy of ego (rollout store)
   const int32_t* env_slots; // optional [bs]: map row of frame b (default b)
+  const int32_t* row_bounds; // optional [bs,E]: rot_row_bounds per env and R row (k_reset); null = no bounds
   float* proj_out;          // optional dump of the pre-rotation grid [bs,C,E,E]
   const float* proj_in;     // optional: take the grid from here instead of scattering
   int stop_after_scatter;   // stage API: return after writing proj_out
@@ -246,6 +248,33 @@ WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const We
   return r;
 }
 
+// Column bounds of the first rotation, one word per R row: first | (last + 1) << 16.
+// R(i,j) samples the fan at (ix, iy) = (h + u*cs + v*sn, h - u*sn + v*cs), u = j - h, v = i - h, h = (E-1)/2 (the
+// affine_grid / unnormalize chain in real arithmetic).  One of its four taps can lie in the fan only if
+// -1 <= iy < fan_rows, ix - iy >= -4 and ix + iy < E + 3; per row each condition is a bound on u.  With 1.5 cells
+// of slack (float rounding is ~1e-4 cells) this is a superset of the cells that hit, so skipping the rest
+// changes nothing: they are the exact zeros the full evaluation would store.  ~70 % of the grid.
+// Evaluated once per env by k_reset (not per slab CTA), read by k_fused.
+WSMG_HD int32_t rot_row_bounds(const Geo& g, float cs1, float sn1, int row) {
+  const int E = g.E;
+  const float h = g.half, m = 1.5f, v = (float)row - h;
+  float lo = -4.0f * (float)E, hi = 4.0f * (float)E;
+  bool none = false;
+  auto bound = [&](float a, float b) {                        // a*u >= b
+    if (a > 1e-3f) lo = fmaxf(lo, b / a);
+    else if (a < -1e-3f) hi = fminf(hi, b / a);
+    else if (b > 1.0f) none = true;                          // |a*u| <= 0.1 everywhere on the grid
+  };
+  bound(-sn1, -1.0f - m - h - v * cs1);                                      // iy >= -1 - m
+  bound(sn1, -((float)g.fan_rows + m) + h + v * cs1);                        // iy <= fan_rows + m
+  bound(cs1 + sn1, -4.0f - m - v * (sn1 - cs1));                             // ix - iy >= -4 - m
+  bound(sn1 - cs1, -((float)E + 3.0f + m) + 2.0f * h + v * (sn1 + cs1));     // ix + iy <= E + 3 + m
+  int jlo = (int)floorf(lo + h) - 1, jhi1 = (int)ceilf(hi + h) + 2;
+  jlo = jlo < 0 ? 0 : jlo; jhi1 = jhi1 > E ? E : jhi1;
+  if (none || jlo >= jhi1) { jlo = 0; jhi1 = 0; }
+  return jlo | (jhi1 << 16);
+}
+
 // ------------------------------------------------------------------ the CTA body
 // NT: threads per CTA (1 in the emulation).  CE/CG/CHW > 0: ego size, global size and Hf*Wf known
 // at compile time (the reference's 100 / 240 / 224*224); 0: read from p.g.
@@ -298,6 +327,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   I2* rowE = fanrow;                                          // per window row: merged extent of its two source R rows (fanrow is dead by then)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);   // one mbarrier per band (TMA)
   float* scal = reinterpret_cast<float*>(bars + MAX_BANDS);   // {cos, sin}(-compass), {cos, sin}(+compass), env flags
+  int32_t* hitrow = reinterpret_cast<int32_t*>(scal + 8);      // per R row: first | (last + 1) << 16 column that can see the fan
   if (WSMG_SKIP(4096)) return;
 
   // ---- per-env scalars that later phases need: fetched and evaluated now by three lanes of three different
@@ -406,6 +436,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   }
   if (tid == 0) { X[0] = f4_zero(); Pf[0] = f4_zero(); }
   for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
+  for (int t = tid; t < E; t += NT) hitrow[t] = p.row_bounds != nullptr ? p.row_bounds[(size_t)b * E + t] : (E << 16);
   for (int t = tid; t < (WSMG_SKIP(2048) ? 0 : SLAB * npp); t += NT) Pk[t] = KEY_EMPTY;
   WSMG_SYNC();
 
@@ -587,7 +618,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const int slot = s0 + tid;
     bool hit = false;
     int i = 0, j = 0;
-    if (slot < nslots && tile_cell(slot, E, &i, &j)) {
+    bool in_tile = slot < nslots && tile_cell(slot, E, &i, &j);
+    if (in_tile) {
+      const int hr = hitrow[i];
+      if (j < (hr & 0xFFFF) || j >= (hr >> 16)) { X[1 + i * E + j] = f4_zero(); in_tile = false; }   // cannot see the fan
+    }
+    if (in_tile) {
       const int t = i * E + j;
       float ix, iy;
       rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);

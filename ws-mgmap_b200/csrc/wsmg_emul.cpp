@@ -71,7 +71,17 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
       for (size_t i = 0; i < per_env; ++i) base[i] = (m == 0.0f) ? 0.0f : base[i] * m;
     }
   }
+  std::vector<int32_t> bounds((size_t)d->bs * g.E, g.E << 16);
+  if (mode != 1) {                                 // what k_reset computes per env
+    for (int b = 0; b < d->bs; ++b) {
+      float cs, sn;
+      if (trig) { cs = trig[4 * b + 0]; sn = trig[4 * b + 1]; }
+      else { const float h = -compass[b]; sn = sinf(h); cs = cosf(h); }
+      for (int t = 0; t < g.E; ++t) bounds[(size_t)b * g.E + t] = rot_row_bounds(g, cs, sn, t);
+    }
+  }
   FusedParams p{};
+  p.row_bounds = bounds.data();
   p.feat = feat; p.codes = codes.data(); p.env_flags = flags.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
   p.ego = ego_out; p.proj_out = proj_out; p.proj_in = (mode == 2) ? proj_in : nullptr;
   p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g; p.sp = sp; p.ego_half = ego_half; p.env_slots = env_slots;
