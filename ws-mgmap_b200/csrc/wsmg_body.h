@@ -241,10 +241,32 @@ WSMG_HD bool tile_cell(int slot, int E, int* i, int* j) {
 }
 WSMG_HD int tile_slots(int E) { return ((E + 7) >> 3) * ((E + 3) >> 2) * 32; }
 
+#if defined(__CUDA_ARCH__)
+// Two channels per instruction: Blackwell's packed-fp32 pipe (FMUL2 / FFMA2) evaluates the blend4 chain of
+// wsmg_math.h -- r = a*nw; r = fma(b, ne, r); r = fma(c, sw, r); r = fma(d, se, r), each step rounded to nearest --
+// on a register pair, bit-identical per channel, at half the issue slots (the kernel is issue-bound).
+__device__ __forceinline__ void blend_pair(float a0, float a1, float b0, float b1, float c0, float c1, float d0, float d1,
+                                           const Weights& w, float* r0, float* r1) {
+  asm("{\n .reg .b64 a, b, c, d, wn, we, ws, wd, r;\n"
+      " mov.b64 a, {%2, %3};\n mov.b64 b, {%4, %5};\n mov.b64 c, {%6, %7};\n mov.b64 d, {%8, %9};\n"
+      " mov.b64 wn, {%10, %10};\n mov.b64 we, {%11, %11};\n mov.b64 ws, {%12, %12};\n mov.b64 wd, {%13, %13};\n"
+      " mul.rn.f32x2 r, a, wn;\n fma.rn.f32x2 r, b, we, r;\n fma.rn.f32x2 r, c, ws, r;\n fma.rn.f32x2 r, d, wd, r;\n"
+      " mov.b64 {%0, %1}, r;\n}\n"
+      : "=f"(*r0), "=f"(*r1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1), "f"(d0), "f"(d1), "f"(w.nw), "f"(w.ne), "f"(w.sw), "f"(w.se));
+}
+#endif
+
 WSMG_HD F4 blend_f4(const F4& a, const F4& b, const F4& c, const F4& d, const Weights& w) {
   F4 r;
+#if defined(__CUDA_ARCH__)
+  static_assert(SLAB == 4, "blend_f4 pairs the four channels of a slab");
+  blend_pair(a.v[0], a.v[1], b.v[0], b.v[1], c.v[0], c.v[1], d.v[0], d.v[1], w, &r.v[0], &r.v[1]);
+  blend_pair(a.v[2], a.v[3], b.v[2], b.v[3], c.v[2], c.v[3], d.v[2], d.v[3], w, &r.v[2], &r.v[3]);
+#else
 #pragma unroll
   for (int ch = 0; ch < SLAB; ++ch) r.v[ch] = blend4(a.v[ch], b.v[ch], c.v[ch], d.v[ch], w.nw, w.ne, w.sw, w.se);
+#endif
   return r;
 }
 
