@@ -771,6 +771,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         }
         if (changed) {             // cells the observation does not raise keep their bytes: no store, no DRAM write
           *cellp = f;
+          if (TMA) fence_proxy_async();   // writer-side: this generic write precedes the TMA load that later recycles the row
           float* dst = gmap_b + ((size_t)(u0 + uu) * G + (v0 + vv)) * C;
           if (VEC) {
             *reinterpret_cast<F4*>(dst) = f;
@@ -808,7 +809,6 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       if (k < NB) {
         if (!WSMG_SKIP(64)) mbar_wait(&bars[k], 0);
         if (!WSMG_SKIP(32)) fuse_band(k);
-        fence_proxy_async();       // generic writes to ring rows precede the TMA load that recycles them
       }
     } else {
       if (k + 2 < NB) prefetch_band(k + 2);
