@@ -1,7 +1,7 @@
 // libwsmg.so -- WS-MGMap per-step map update for B200 (sm_100a).  C ABI in include/wsmg.h.
 //
 // Three launches per step, all on the caller's stream:
-//   k_reset   episode-reset mask over the whole NHWC map       (rgb_mapping.py:35)
+//   k_reset   episode-reset mask over the whole NHWC map       (rgb_mapping.py:35); per-env rotation column bounds
 //   k_cells   fused unproject + height-band test + bin + index  (rgb_mapping.py:153-176, 188-217)
 //   k_fused   one CTA per (env, 4-channel slab): shared-memory scatter-max, rotate, translate,
 //             max-fuse into the map window, translate back, crop, rotate -> NCHW ego map
@@ -172,7 +172,7 @@ static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8
   return (int)cudaGetLastError();
 }
 
-// CUtensorMap of the caller's NHWC map [n_maps, G, G, C] with a one-window-row box {4 ch, E+2 cols, 1, 1}.
+// CUtensorMap of the caller's NHWC map [n_maps, G, G, C] with a box of {4 ch, WWP cols, TMA_ROWS rows, 1}.
 // cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
 static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const Geo& g) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

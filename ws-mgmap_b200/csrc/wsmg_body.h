@@ -3,31 +3,32 @@
 //   * by g++ as a serial emulation (wsmg_emul.cpp, NT = 1) that the CPU tests compare against
 //     the oracle.  The emulation is test infrastructure; nothing in the product path calls it.
 //
-// Design rules that came out of the ncu captures under profiles/ (the kernel was, in turn, instruction-issue
-// bound, LSU-wavefront bound and finally latency/barrier bound at the 32 warps one 231 KB CTA leaves an SM):
+// Design rules that came out of the ncu captures under profiles/ (the kernel is bound per SM -- instruction
+// issue, LSU wavefronts and the barriers between phases at the 32 warps one 229 KB CTA leaves an SM -- not by DRAM):
 //   * CTA size, ego/global size and the feature-plane stride are template constants for the reference
 //     shapes; single-trip loops collapse to an `if`, divisions to multiplies, plane offsets to immediates;
 //   * every bilinear tap is `table entry + table entry -> LDS.128`, index <= 0 meaning "zero": out-of-range
 //     taps, taps whose weight is exactly 0 (two thirds of the translate rows/columns) and taps outside the
-//     fan are never read;
-//   * the NHWC map window moves with TMA row boxes (no LSU), the feature planes with per-thread cp.async
-//     slots staged in the not-yet-used X buffer;
+//     fan are never read; the blend runs on the packed fp32 pipe (FMUL2 / FFMA2, two channels per instruction);
+//   * the NHWC map window is loaded with TMA boxes (no LSU) and only the cells an observation raises are
+//     stored back, straight from the fuse; the feature planes move with per-thread cp.async slots staged in
+//     the not-yet-used X buffer;
 //   * the scatter reduces runs of equal cells in registers and issues plain shared atomics on signed keys
-//     for which a non-negative float is its own key (profiles/: match_any+redux aggregation is 39x slower).
+//     for which a non-negative float is its own key (profiles/: match_any+redux aggregation is 39x slower);
+//     its loop is statically strided and unrolled so that queues and slots are register names.
 //
-// Shared memory (E=100, G=240: 231968 of the 232448 bytes a CTA may opt in to):
+// Shared memory (E=100, G=240: 229 KB of the 227 KiB a CTA may opt in to):
 //   X     [1 + E*E] F4    zero cell + (during the scatter) the per-thread cp.async feature slots, then the
 //                         rotated ego grid R; its rows are overwritten by the crop B behind the fuse front
 //   Z     1 F4            zero cell shared by the fan and the F ring (sits right before R2)
 //   R2    scatter: planar signed-int keys [4][npp], then F4[fan_cells];
-//         afterwards: F ring, `rr` window rows of WWP cells (128-byte aligned rows).  Each row of
-//         the caller's map window is a TMA box {4 ch, WW cols, 1 row} copied straight into its
-//         ring row (mbarrier complete_tx; out-of-map cells arrive as zeros), max-fused IN PLACE
-//         and TMA-stored back (out-of-map cells are clipped): the 16-byte-per-cell NHWC gather
-//         never touches the LSU.  Band 0 lands beyond the key planes so that it streams in
-//         underneath the scatter.  (C % 4 != 0: cp.async / st.global fallback.)
+//         afterwards: F ring, `rr` window rows of WWP cells (128-byte aligned rows).  The caller's map
+//         window arrives as TMA boxes {4 ch, WWP cols, TMA_ROWS rows} copied straight into ring rows
+//         (mbarrier complete_tx; cells outside the map arrive as zeros) and is max-fused IN PLACE; raised
+//         cells go back with one 16-byte st.global each.  Band 0 lands beyond the key planes so that it
+//         streams in underneath the scatter.  (C % 4 != 0: cp.async loads instead of TMA.)
 //   T     colT[WW], rowT[WW], bXT[E], bYT[E] (I4 each): the two separable translations
-//   tail  baseE[E], fanrow[E+1] (later rowE[E+2]), ext[E], mbarriers + the scatter's chunk counter
+//   tail  baseE[E], fanrow[E+1] (later rowE[E+2]), ext[E], mbarriers, per-CTA scalars, hitrow[E]
 #pragma once
 #include "wsmg_math.h"
 #if defined(__CUDACC__)
