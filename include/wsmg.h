@@ -162,6 +162,20 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
                             float* ego_out_host, void* staging, size_t staging_bytes,
                             int32_t chunk_envs, const wsmg_dims* d, uint32_t flags, void* stream);
 
+/* Ground-truth semantic map sensor, batched.  Replaces the per-env, per-step CPU work of
+ * GtSemanticMapSensor.get_observation, habitat_extensions/sensors.py:403-410:
+ *   grid_sample(grid_sample(map, trans_grid, nearest), rot_grid, nearest), pad by `half`, crop
+ *   [origin-half, origin+half)^2, .long()
+ * maps   [n_maps,S,S] fp32 class ids (the episode's map, already rotated by the start heading, sensors.py:390-392)
+ * pose   [bs,3] fp32 = ((grid_y-S/2)/(S/2), (grid_x-S/2)/(S/2), -heading)        (sensors.py:397-401)
+ * trig   optional [bs,2] fp32 = (cos, sin) of pose[:,2] as the caller's host evaluated them (bit-exact parity with
+ *        the reference's CPU result); NULL: cosf/sinf on the device
+ * map_index optional [bs] int32: which map each frame reads (default b)
+ * out    [bs,2*half,2*half] int64.  All pointers device memory; stream-ordered. */
+int wsmg_semantic_crop(const float* maps, const float* pose, const float* trig, const int32_t* map_index,
+                       int64_t* out, int32_t bs, int32_t n_maps, int32_t S, int32_t half, int32_t origin,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,65 @@ def make_reference_mapper(num_proc, **kw):
     finally:
         mod.torch.device = orig
     return m, mod
+
+
+# ------------------------------------------------------------------ the ground-truth semantic map sensor
+SENSOR_FILE = "/root/reference/habitat_extensions/sensors.py"
+
+
+def sensor_reference_available() -> bool:
+    return os.path.isfile(SENSOR_FILE) and reference_available()
+
+
+class ReferenceSemMapSensor:
+    """Runs the UNMODIFIED body of `GtSemanticMapSensor.get_observation` (sensors.py:383-410) without Habitat:
+    the method's source is cut out of the reference file with `ast` and compiled as is; the simulator, the episode
+    and `np.load` are replaced by stand-ins that hand it the arrays a test chose.  Everything the method computes
+    with (`get_grid`, `F.grid_sample`, `F.pad`) is the real thing."""
+
+    def __init__(self, half_size: int = 50):
+        import ast
+        import numpy as np
+        import torch.nn.functional as F
+        src = open(SENSOR_FILE).read()
+        tree = ast.parse(src)
+        fn = None
+        for node in ast.walk(tree):
+            if isinstance(node, ast.ClassDef) and node.name == "GtSemanticMapSensor":
+                for item in node.body:
+                    if isinstance(item, ast.FunctionDef) and item.name == "get_observation":
+                        fn = item
+        assert fn is not None, "GtSemanticMapSensor.get_observation not found in the reference"
+        fn.decorator_list = []
+        mod = ast.Module(body=[fn], type_ignores=[])
+        ast.fix_missing_locations(mod)
+        ref_mod = load_reference_module()
+        outer = self
+
+        class _Np:                      # numpy, except that np.load returns the map the test supplies
+            def __getattr__(self, name):
+                return getattr(np, name)
+
+            @staticmethod
+            def load(path):
+                return outer._map_to_load
+
+        ns = {"torch": torch, "F": F, "np": _Np(), "os": os, "get_grid": ref_mod.get_grid, "Any": object}
+        exec(compile(mod, SENSOR_FILE, "exec"), ns)
+        self._method = ns["get_observation"]
+        self.half_size = half_size
+        self.gt_path = "unused"
+        self.prev_episode_id = None
+        self._map_to_load = None
+        self._sim = types.SimpleNamespace(record_heading=0.0, _state=None)
+        self._sim.get_agent_state = lambda: self._sim._state
+
+    def observe(self, episode_id, position, heading, new_map=None):
+        """position: (x, y, z) of the agent; heading: the simulator's record_heading; new_map: int array [S,S]
+        returned by np.load when the episode id changes."""
+        self._map_to_load = new_map
+        self._sim.record_heading = float(heading)
+        self._sim._state = types.SimpleNamespace(position=[float(p) for p in position])
+        episode = types.SimpleNamespace(episode_id=episode_id)
+        return self._method(self, None, episode)
+

@@ -58,3 +58,17 @@ def emul_step(gmap, feat, depth, gps, compass, masks, trig=None, mode=0, proj_in
                               _p(None if env_slots is None else np.ascontiguousarray(env_slots, np.int32)))
     assert rc == 0, rc
     return ego, proj
+
+
+def emul_semantic_crop(maps, pose, trig=None, map_index=None, half=50, origin=289):
+    maps = np.ascontiguousarray(maps, np.float32)
+    pose = np.ascontiguousarray(pose, np.float32)
+    bs = pose.shape[0]
+    out = np.zeros((bs, 2 * half, 2 * half), np.int64)
+    trig_a = None if trig is None else np.ascontiguousarray(trig, np.float32)
+    mi = None if map_index is None else np.ascontiguousarray(map_index, np.int32)
+    rc = lib().wsmg_emul_semantic_crop(_p(maps), _p(pose), _p(trig_a), _p(mi), _p(out), ctypes.c_int32(bs),
+                                       ctypes.c_int32(maps.shape[0]), ctypes.c_int32(maps.shape[1]), ctypes.c_int32(half),
+                                       ctypes.c_int32(origin))
+    assert rc == 0, rc
+    return out

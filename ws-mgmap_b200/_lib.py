@@ -40,6 +40,8 @@ SIGNATURES = {
     "wsmg_base_coords_host": (ctypes.c_int, [_P, ctypes.c_int32]),
     "wsmg_host_staging_bytes": (ctypes.c_size_t, [_DP, ctypes.c_int32]),
     "wsmg_map_update_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP, _P]),
+    "wsmg_semantic_crop": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_int32, _P]),
     "wsmg_map_update_host_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP,
                                                ctypes.c_uint32, _P]),
 }

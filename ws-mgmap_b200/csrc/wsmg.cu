@@ -145,6 +145,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constan
   fused_body<FUSED_THREADS, CE, CG, CHW, VEC, TMA, POOL>(p, blockIdx.x, smem, threadIdx.x);
 }
 
+// ------------------------------------------------------------------ k_semcrop
+// The ground-truth semantic map sensor for a batch of envs: one thread per output cell, two chained nearest
+// resamplings collapsed into one gather (sensors.py:403-410).  4*half^2 cells per env: latency-bound, tiny.
+__global__ void __launch_bounds__(256) k_semcrop(const float* __restrict__ maps, const float* __restrict__ pose,
+                                                 const float* __restrict__ trig, const int32_t* __restrict__ map_index,
+                                                 long long* __restrict__ out, int n_maps, int S, int half, int origin) {
+  const int b = blockIdx.y, side = 2 * half;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= side * side) return;
+  float cs, sn;
+  if (trig != nullptr) { cs = trig[2 * b]; sn = trig[2 * b + 1]; }
+  else { const float h = pose[3 * b + 2]; cs = cosf(h); sn = sinf(h); }
+  const int i = t / side, j = t - i * side;
+  const int idx = semmap_source_index(origin - side + i, origin - side + j, S, cs, sn, pose[3 * b], pose[3 * b + 1]);
+  const int m = map_index != nullptr ? map_index[b] : b;
+  long long v = 0;
+  if (idx >= 0 && (unsigned)m < (unsigned)n_maps) v = (long long)maps[(size_t)m * S * S + idx];
+  out[(size_t)b * side * side + t] = v;
+}
+
 // ------------------------------------------------------------------ host glue
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -477,6 +497,18 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
   cudaEventDestroy(fork);
   if (rc == 0) rc = (int)cudaGetLastError();
   return rc;
+}
+
+int wsmg_semantic_crop(const float* maps, const float* pose, const float* trig, const int32_t* map_index, int64_t* out,
+                       int32_t bs, int32_t n_maps, int32_t S, int32_t half, int32_t origin, void* stream) {
+  if (!maps || !pose || !out) return WSMG_E_NULL;
+  if (bs <= 0 || n_maps <= 0 || S <= 0 || S > 32768 || half <= 0 || half > 16384) return WSMG_E_DIMS;
+  if (map_index == nullptr && n_maps < bs) return WSMG_E_BATCH;
+  const int cells = 4 * half * half;
+  dim3 grid((cells + 255) / 256, bs);
+  k_semcrop<<<grid, 256, 0, (cudaStream_t)stream>>>(maps, pose, trig, map_index, reinterpret_cast<long long*>(out), n_maps, S,
+                                                     half, origin);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -100,6 +100,24 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
   return 0;
 }
 
+// host mirror of k_semcrop (wsmg.cu)
+int wsmg_emul_semantic_crop(const float* maps, const float* pose, const float* trig, const int32_t* map_index, int64_t* out,
+                            int32_t bs, int32_t n_maps, int32_t S, int32_t half, int32_t origin) {
+  const int side = 2 * half;
+  for (int b = 0; b < bs; ++b) {
+    float cs, sn;
+    if (trig) { cs = trig[2 * b]; sn = trig[2 * b + 1]; }
+    else { const float h = pose[3 * b + 2]; cs = cosf(h); sn = sinf(h); }
+    const int m = map_index ? map_index[b] : b;
+    for (int t = 0; t < side * side; ++t) {
+      const int i = t / side, j = t - i * side;
+      const int idx = semmap_source_index(origin - side + i, origin - side + j, S, cs, sn, pose[3 * b], pose[3 * b + 1]);
+      out[(size_t)b * side * side + t] = (idx >= 0 && (unsigned)m < (unsigned)n_maps) ? (int64_t)maps[(size_t)m * S * S + idx] : 0;
+    }
+  }
+  return 0;
+}
+
 int wsmg_emul_smem_bytes(const wsmg_dims* d) {
   if (validate_dims(d)) return -1;
   return make_plan(make_geo(d)).total;

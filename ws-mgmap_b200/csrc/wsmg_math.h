@@ -175,4 +175,27 @@ WSMG_HD bool unproject_pixel(const Geo& g, const float* depth_b, int i, int j, i
   return ok;
 }
 
+// ---- ground-truth semantic map sensor (habitat_extensions/sensors.py:403-410) --------------------------
+// One cell of `grid_sample(grid_sample(map, trans_grid, nearest), rot_grid, nearest)`: (r, c) is the cell of the
+// rotated map; returns the linear index into the S x S source map, or -1 when either resampling lands outside
+// (zeros padding).  rot_grid = affine_grid([[cos, -sin, 0], [sin, cos, 0]]) through the K=3 bmm
+// (gx = fma(y, -sin, x*cos), gy = fma(y, cos, x*sin)); trans_grid = base + (tx, ty) (rgb_mapping.py:106-139);
+// nearest = unnormalize, then round half to even.
+WSMG_HD int nearest_index(float g, int size, float half_size) {
+  const float r = rintf(unnormalize(g, half_size));
+  return (r > -1.0f && r < (float)size) ? (int)r : -1;
+}
+WSMG_HD int semmap_source_index(int r, int c, int S, float cs, float sn, float tx, float ty) {
+  if ((unsigned)r >= (unsigned)S || (unsigned)c >= (unsigned)S) return -1;     // the zero padding of sensors.py:406
+  const float hs = (float)S / 2.0f;
+  const float bx = base_coord(c, S), by = base_coord(r, S);
+  const int x1 = nearest_index(fmaf(by, -sn, bx * cs), S, hs);
+  const int y1 = nearest_index(fmaf(by, cs, bx * sn), S, hs);
+  if (x1 < 0 || y1 < 0) return -1;
+  const int x2 = nearest_index(base_coord(x1, S) + tx, S, hs);
+  const int y2 = nearest_index(base_coord(y1, S) + ty, S, hs);
+  if (x2 < 0 || y2 < 0) return -1;
+  return y2 * S + x2;
+}
+
 }  // namespace wsmg

@@ -108,6 +108,27 @@ def register_fuse_retrieve(proj, gps, compass, mask, gmap, resolution=0.12, trig
     return ego
 
 
+def semantic_crop(maps, pose, half=50, origin=289, trig=None, map_index=None):
+    """Batched ground-truth semantic map sensor (habitat_extensions/sensors.py:403-410, wsmg_semantic_crop).
+    maps [n,S,S] fp32 CUDA class ids, pose [bs,3] fp32 CUDA = ((grid_y-S/2)/(S/2), (grid_x-S/2)/(S/2), -heading),
+    trig optional [bs,2] (cos, sin of pose[:,2]), map_index optional int32 [bs].  Returns int64 [bs,2*half,2*half]."""
+    lib = _lib.load()
+    if not (maps.is_cuda and pose.is_cuda and maps.dtype == torch.float32 and pose.dtype == torch.float32):
+        raise ValueError("semantic_crop: fp32 CUDA tensors required")
+    if maps.dim() != 3 or maps.shape[1] != maps.shape[2] or pose.dim() != 2 or pose.shape[1] != 3:
+        raise ValueError("semantic_crop: maps [n,S,S], pose [bs,3]")
+    maps, pose = maps.contiguous(), pose.contiguous()
+    bs, dev = pose.shape[0], maps.device
+    out = torch.empty(bs, 2 * half, 2 * half, dtype=torch.int64, device=dev)
+    trig = None if trig is None else trig.to(dev, torch.float32).contiguous()
+    map_index = None if map_index is None else map_index.to(dev, torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.wsmg_semantic_crop(_ptr(maps), _ptr(pose), _ptr(trig), _ptr(map_index), _ptr(out), bs, maps.shape[0],
+                                    maps.shape[1], half, origin, _stream(dev))
+    _lib.check(rc, "wsmg_semantic_crop")
+    return out
+
+
 class HostPipeline:
     """End-to-end step from HOST (pinned) buffers: H2D of the frame, update, D2H of the ego map,
     chunked so copies overlap the kernels (wsmg_map_update_host_ex).  zero_copy=True: the feature tensor must be
