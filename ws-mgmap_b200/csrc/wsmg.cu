@@ -25,7 +25,8 @@ constexpr int CELLS_THREADS = 256;
 __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
                                                size_t per_env, uint32_t* __restrict__ env_flags,
                                                const int32_t* __restrict__ env_slots, int32_t* __restrict__ row_bounds,
-                                               const float* __restrict__ compass, const float* __restrict__ trig, Geo g) {
+                                               float* __restrict__ env_trig, const float* __restrict__ compass,
+                                               const float* __restrict__ trig, Geo g) {
   const int b = blockIdx.y;
   if (env_flags != nullptr && blockIdx.x == 0 && threadIdx.x == 0) env_flags[b] = 0u;   // k_cells (next launch) sets them
   if (row_bounds != nullptr && blockIdx.x == gridDim.x - 1) {     // per-env column bounds of the first rotation (wsmg_body.h)
@@ -33,6 +34,12 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
     if (trig != nullptr) { cs = trig[4 * b + 0]; sn = trig[4 * b + 1]; }
     else { const float h = -compass[b]; sn = sinf(h); cs = cosf(h); }
     for (int t = threadIdx.x; t < g.E; t += blockDim.x) row_bounds[(size_t)b * g.E + t] = rot_row_bounds(g, cs, sn, t);
+    if (env_trig != nullptr && threadIdx.x == 0) {             // both rotations' cos / sin, exactly as k_fused would evaluate them
+      float cs2, sn2;
+      if (trig != nullptr) { cs2 = trig[4 * b + 2]; sn2 = trig[4 * b + 3]; }
+      else { const float h = compass[b]; sn2 = sinf(h); cs2 = cosf(h); }
+      env_trig[4 * b + 0] = cs; env_trig[4 * b + 1] = sn; env_trig[4 * b + 2] = cs2; env_trig[4 * b + 3] = sn2;
+    }
   }
   if (gmap == nullptr) return;
   const float m = mask[b];
@@ -169,11 +176,11 @@ __global__ void __launch_bounds__(256) k_semcrop(const float* __restrict__ maps,
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const int32_t* env_slots, const wsmg_dims* d,
-                        cudaStream_t s, int32_t* row_bounds = nullptr, const float* compass = nullptr,
-                        const float* trig = nullptr) {
+                        cudaStream_t s, int32_t* row_bounds = nullptr, float* env_trig = nullptr,
+                        const float* compass = nullptr, const float* trig = nullptr) {
   const size_t per_env = (size_t)d->G * d->G * d->C;
   dim3 grid(gmap ? 16 : 1, d->bs);
-  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags, env_slots, row_bounds, compass, trig, make_geo(d));
+  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags, env_slots, row_bounds, env_trig, compass, trig, make_geo(d));
   return (int)cudaGetLastError();
 }
 
@@ -313,12 +320,14 @@ static int map_update_impl(const float* feat, const float* depth, const float* g
   uint16_t* codes = (uint16_t*)scratch;
   uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
   int32_t* bounds = (int32_t*)((unsigned char*)flags + scratch_flags_bytes(d));
-  rc = launch_reset(gmap, mask, flags, env_slots, d, s, bounds, compass, trig);
+  float* env_trig = (float*)((unsigned char*)bounds + scratch_bounds_bytes(d));
+  rc = launch_reset(gmap, mask, flags, env_slots, d, s, bounds, env_trig, compass, trig);
   if (rc) return rc;
   rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
   p.row_bounds = bounds;
+  p.env_trig = env_trig;
   p.feat = feat; p.codes = codes; p.env_flags = flags; p.gps = gps; p.compass = compass; p.trig = trig;
   p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
   p.ego_half = (uint16_t*)ego_half; p.env_slots = env_slots;

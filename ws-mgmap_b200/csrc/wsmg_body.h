@@ -141,6 +141,7 @@ struct FusedParams {
   uint16_t* ego_half;       // optional [bs,C,E,E] IEEE binary16 copy of ego (rollout store)
   const int32_t* env_slots; // optional [bs]: map row of frame b (default b)
   const int32_t* row_bounds; // optional [bs,E]: rot_row_bounds per env and R row (k_reset); null = no bounds
+  const float* env_trig;    // optional [bs,4]: {cos, sin}(-compass), {cos, sin}(+compass) per env (k_reset); null = evaluate here
   float* proj_out;          // optional dump of the pre-rotation grid [bs,C,E,E]
   const float* proj_in;     // optional: take the grid from here instead of scattering
   int stop_after_scatter;   // stage API: return after writing proj_out
@@ -358,7 +359,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // after a barrier (rgb_mapping.py:37,70 -> :239-245)
   {
     const int t_r1 = 0, t_r2 = NT > 64 ? 32 : 0, t_fl = NT > 64 ? 64 : 0;
-    if (!p.stop_after_scatter) {
+    if (!p.stop_after_scatter && p.env_trig != nullptr) {          // evaluated once per env by k_reset
+      if (tid < 4) scal[tid] = p.env_trig[4 * b + tid];
+    } else if (!p.stop_after_scatter) {
       if (tid == t_r1) {
         float cs_, sn_;
         if (p.trig != nullptr) { cs_ = p.trig[4 * b + 0]; sn_ = p.trig[4 * b + 1]; }

@@ -67,14 +67,15 @@ inline const char* error_string(int code) {
   }
 }
 
-// scratch layout: [bs * Hf*Wf] uint16 packed cell codes | [bs] uint32 env flags | [bs * E] int32 rotation column bounds
+// scratch layout: [bs * Hf*Wf] uint16 packed cell codes | [bs] uint32 env flags | [bs * E] int32 rotation column bounds | [bs * 4] fp32 rotation sines / cosines
 inline size_t scratch_codes_bytes(const wsmg_dims* d) {
   size_t codes = (size_t)d->bs * d->Hf * d->Wf * sizeof(uint16_t);
   return (codes + 255) & ~(size_t)255;
 }
 inline size_t scratch_flags_bytes(const wsmg_dims* d) { return ((size_t)d->bs * sizeof(uint32_t) + 255) & ~(size_t)255; }
+inline size_t scratch_bounds_bytes(const wsmg_dims* d) { return ((size_t)d->bs * d->E * sizeof(int32_t) + 255) & ~(size_t)255; }
 inline size_t scratch_bytes(const wsmg_dims* d) {
-  return scratch_codes_bytes(d) + scratch_flags_bytes(d) + (((size_t)d->bs * d->E * sizeof(int32_t) + 255) & ~(size_t)255);
+  return scratch_codes_bytes(d) + scratch_flags_bytes(d) + scratch_bounds_bytes(d) + (((size_t)d->bs * 4 * sizeof(float) + 255) & ~(size_t)255);
 }
 
 inline void base_coords_host(float* out, int n) {
