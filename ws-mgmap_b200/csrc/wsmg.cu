@@ -75,13 +75,15 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
 // write" flag (those pixels send the sentinel to cell 0, rgb_mapping.py:207-212).
 constexpr int CELLS_PX = 4;
 constexpr int CELLS_MAX_W = 1024;
+// STAGE_API: also write the reference-shaped (lin, invalid) arrays (stage entry point only; the step never does).
+template <bool STAGE_API>
 __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
                                                           int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
                                                           uint32_t* __restrict__ env_flags, Geo g, int stage_rows) {
   extern __shared__ __align__(128) unsigned char cells_smem[];
   __shared__ int rowoff[160];
-  __shared__ int col_src[CELLS_MAX_W];
-  __shared__ float col_xx[CELLS_MAX_W];
+  __shared__ __align__(16) int col_src[CELLS_MAX_W];
+  __shared__ __align__(16) float col_xx[CELLS_MAX_W];
   __shared__ __align__(8) uint64_t bar;
   float* drows = reinterpret_cast<float*>(cells_smem);       // [stage_rows][Wd] when stage_rows > 0
   const int b = blockIdx.y;
@@ -115,22 +117,43 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   float yy = pinhole_yy(g, r);
   uint32_t code[CELLS_PX];
   bool any_bad = false, any_outlier = false;
-#pragma unroll
-  for (int px = 0; px < CELLS_PX; ++px) {
-    const int t = t0 + px;
+  auto one_pixel = [&](int px, int t, float dval, float xx) {
+    int x, y;
+    const bool ok = unproject_depth(g, dval, xx, yy, &x, &y);
+    any_bad |= !ok;
     code[px] = CODE_INVALID;
-    if (t < HW) {
-      int x, y;
-      const float dval = staged ? drows[(r - r_first) * g.Wd + col_src[j]] : depth_b[(size_t)r * g.Wd + col_src[j]];
-      const bool ok = unproject_depth(g, dval, col_xx[j], yy, &x, &y);
-      any_bad |= !ok;
-      if (ok) {
-        if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
-        else { code[px] = CODE_OUTLIER; any_outlier = true; }
-      }
+    if (ok) {
+      if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
+      else { code[px] = CODE_OUTLIER; any_outlier = true; }
+    }
+    if (STAGE_API) {
       if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
       if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
-      if (++j == g.Wf) { j = 0; ++i; r = sample_index(g, i); yy = pinhole_yy(g, r); }
+    }
+  };
+  if ((g.Wf & 3) == 0 && t0 + CELLS_PX <= HW) {
+    // the four pixels share a row: one row pointer, the column tables as two 16-byte reads
+    const int4 cs = *reinterpret_cast<const int4*>(&col_src[j]);
+    const float4 cx = *reinterpret_cast<const float4*>(&col_xx[j]);
+    float d0, d1, d2, d3;
+    if (staged) {                                            // (kept apart so that the staged reads are LDS, not generic loads)
+      const float* row = drows + (r - r_first) * g.Wd;
+      d0 = row[cs.x]; d1 = row[cs.y]; d2 = row[cs.z]; d3 = row[cs.w];
+    } else {
+      const float* row = depth_b + (size_t)r * g.Wd;
+      d0 = __ldg(row + cs.x); d1 = __ldg(row + cs.y); d2 = __ldg(row + cs.z); d3 = __ldg(row + cs.w);
+    }
+    one_pixel(0, t0, d0, cx.x); one_pixel(1, t0 + 1, d1, cx.y); one_pixel(2, t0 + 2, d2, cx.z); one_pixel(3, t0 + 3, d3, cx.w);
+  } else {
+#pragma unroll
+    for (int px = 0; px < CELLS_PX; ++px) {
+      const int t = t0 + px;
+      code[px] = CODE_INVALID;
+      if (t < HW) {
+        const float dval = staged ? drows[(r - r_first) * g.Wd + col_src[j]] : depth_b[(size_t)r * g.Wd + col_src[j]];
+        one_pixel(px, t, dval, col_xx[j]);
+        if (++j == g.Wf) { j = 0; ++i; r = sample_index(g, i); yy = pinhole_yy(g, r); }
+      }
     }
   }
   if (codes != nullptr && t0 < HW) {       // HW % 4 == 0 (validated): the four codes are one aligned 8-byte word
@@ -195,7 +218,8 @@ static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8
   size_t smem = (size_t)stage_rows * g.Wd * 4;
   const bool bulk_ok = (g.Wd % 4) == 0 && (((size_t)g.Hd * g.Wd) % 4) == 0 && (reinterpret_cast<uintptr_t>(depth) & 15u) == 0;
   if (smem > 32 * 1024 || !bulk_ok) { stage_rows = 0; smem = 0; }     // fall back to direct global gathers
-  k_cells<<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, g, stage_rows);
+  if (lin != nullptr || invalid != nullptr) k_cells<true><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, g, stage_rows);
+  else k_cells<false><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, g, stage_rows);
   return (int)cudaGetLastError();
 }
 

@@ -57,20 +57,6 @@ struct alignas(16) F4 { float v[4]; };
 struct alignas(16) I4 { int a, b, c, d; };
 struct alignas(8) I2 { int a, b; };
 WSMG_HD F4 f4_zero() { F4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0f; return r; }
-WSMG_HD float as_float(int i) {
-#if defined(__CUDA_ARCH__)
-  return __int_as_float(i);
-#else
-  float f; __builtin_memcpy(&f, &i, 4); return f;
-#endif
-}
-WSMG_HD int as_int(float f) {
-#if defined(__CUDA_ARCH__)
-  return __float_as_int(f);
-#else
-  int i; __builtin_memcpy(&i, &f, 4); return i;
-#endif
-}
 WSMG_HD int imax0(int a) { return a > 0 ? a : 0; }
 
 constexpr int fan_cells_of(int E) {

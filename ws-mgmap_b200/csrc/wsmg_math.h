@@ -148,15 +148,37 @@ WSMG_HD float pinhole_yy(const Geo& g, int r) { return ((float)(g.Hd - r) - g.cy
 // (tests: bit-exact cell indices against the oracle's true division, incl. half-cell multiples.)
 WSMG_HD float div_cell(const Geo& g, float x) { return (float)((double)x * g.inv_cell); }
 
+// bit casts
+WSMG_HD float as_float(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float f; __builtin_memcpy(&f, &i, 4); return f;
+#endif
+}
+WSMG_HD int as_int(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i; __builtin_memcpy(&i, &f, 4); return i;
+#endif
+}
+
+// rint (half to even) without the conversion unit: for |v| <= 2^22, (v + 1.5*2^23) - 1.5*2^23 is rintf(v) and the
+// low mantissa bits of the sum are the integer itself.  Beyond that range the result is only used for the
+// in-grid test, which both versions fail alike (huge stays huge, NaN stays NaN).
+constexpr float RINT_MAGIC = 12582912.0f;                     // 1.5 * 2^23, bits 0x4B400000
 WSMG_HD bool unproject_depth(const Geo& g, float depth01, float xx, float yy, int* x, int* y) {
   float z = depth01 * 10.0f;                                  // rgb_mapping.py:37
   float X = xx * z, Y = yy * z;
   bool ok = (z != 0.0f) && (Y > -1.5f) && (Y < 0.1f);
-  float xf = rintf(div_cell(g, X) + g.half);
-  float yf = rintf(-div_cell(g, z) + g.half);
-  ok = ok && (xf >= 0.0f) && (xf < (float)g.E) && (yf >= 0.0f) && (yf < (float)g.E);
-  *x = ok ? (int)xf : 0;
-  *y = ok ? (int)yf : 0;
+  const float xs = (div_cell(g, X) + g.half) + RINT_MAGIC;   // rgb_mapping.py:173
+  const float ys = (-div_cell(g, z) + g.half) + RINT_MAGIC;  // rgb_mapping.py:174
+  const float xf = xs - RINT_MAGIC, yf = ys - RINT_MAGIC;
+  const float ef = (float)g.E;
+  ok = ok && (xf >= 0.0f) && (xf < ef) && (yf >= 0.0f) && (yf < ef);
+  *x = ok ? as_int(xs) - 0x4B400000 : 0;
+  *y = ok ? as_int(ys) - 0x4B400000 : 0;
   return ok;
 }
 WSMG_HD bool unproject_pixel(const Geo& g, const float* depth_b, int i, int j, int* x, int* y) {
