@@ -277,7 +277,8 @@ def run_native(args, rank, local_rank, world):
     # ---- end to end from pinned host buffers (`e2e`) ----------------------------------------
     ne = min(n, args.e2e_envs)
     de = ops.dims_for((ne,) + tuple(feat.shape[1:]), depth[:ne].shape, ne, s["E"], s["G"], s["resolution"])
-    pipe = ops.HostPipeline(de, dev, chunk_envs=args.e2e_chunk, zero_copy=args.e2e_mode == "zerocopy")
+    pipe = ops.HostPipeline(de, dev, chunk_envs=args.e2e_chunk, zero_copy=args.e2e_mode == "zerocopy",
+                            skip_dead_rows=args.e2e_mode == "rows")
     feat_h = feat[:ne].cpu().pin_memory()
     depth_h = depth[:ne].cpu().pin_memory()
     gps_h, comp_h, mask_h = (x[:, :ne].contiguous().cpu().pin_memory() for x in (gps, compass, masks))
@@ -294,6 +295,10 @@ def run_native(args, rank, local_rank, world):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     h2d = ne * 4 * (s["C"] * s["Hf"] * s["Wf"] + s["Hd"] * s["Wd"] + 4)
+    if args.e2e_mode == "rows":      # bytes that actually cross the bus: live feature rows + depth + pose
+        lo, hi = ops.host_live_rows(depth_h, de)
+        rows = int((hi - lo + 1).clamp(min=0).sum())
+        h2d = 4 * (rows * s["Wf"] * s["C"] + ne * (s["Hd"] * s["Wd"] + 4))
     d2h = ne * 4 * s["C"] * s["E"] * s["E"]
 
     # ---- per depth distribution (uniform / near / room), short runs on up to 256 envs ----
@@ -365,7 +370,8 @@ def run_native(args, rank, local_rank, world):
                          "whole_step_frac": B * n * world / (max_ms / K / 1e3) / 1e9 / (peak * world)},
             "e2e": {"value": ne * world * Ke / (max_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "envs_per_gpu": ne, "steps": Ke,
-                    "api": "wsmg_map_update_host (pinned host buffers, chunked H2D/compute/D2H)"},
+                    "api": "wsmg_map_update_host_ex (pinned host buffers, chunked H2D/compute/D2H)", "mode": args.e2e_mode,
+                    "h2d_bytes_per_step_dense": ne * 4 * (s["C"] * s["Hf"] * s["Wf"] + s["Hd"] * s["Wd"] + 4) * world},
             "gpu_launches": 3 * K * world,
             "clocks": clk.summary(),
             "checksums": [float(x) for x in allst[:, 3]],
@@ -394,8 +400,9 @@ def main():
     ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU in the host-buffer (e2e) leg")
     ap.add_argument("--e2e-chunk", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-mode", default="copy", choices=["copy", "zerocopy"],
-                    help="host-buffer leg: stage the features with cudaMemcpyAsync, or let the scatter read the pinned buffer")
+    ap.add_argument("--e2e-mode", default="rows", choices=["copy", "rows", "zerocopy"],
+                    help="host-buffer leg: stage the whole feature tensor, only the rows that hold a writing pixel, "
+                         "or let the scatter read the pinned buffer")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per k_fused launch from ncu, if known")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-by-depth", action="store_true", help="skip the per-depth-distribution runs")

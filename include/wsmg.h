@@ -155,8 +155,12 @@ int wsmg_map_update_host(const float* feat_host, const float* depth_host, const 
 /* wsmg_map_update_host with options.  WSMG_HOST_ZEROCOPY_FEATURES: `feat_host` must be page-locked, device-mapped
  * host memory (cudaHostAlloc / cudaHostRegister, torch `pin_memory()`); the scatter then pulls the features over
  * the bus itself and the 4-pixel groups that cannot write (typically 45-50 % of a frame) never cross it.  Replaces
- * the H2D half of batch_obs (common_trainer / dagger_trainer) for the feature tensor.  Everything else as above. */
-enum { WSMG_HOST_ZEROCOPY_FEATURES = 1 };
+ * the H2D half of batch_obs (common_trainer / dagger_trainer) for the feature tensor.
+ * WSMG_HOST_SKIP_DEAD_ROWS: before the copies are queued, the host runs the unprojection test of rgb_mapping.py:165-174
+ * on the depth frame (same arithmetic as the device) and copies, per env, only the feature rows between the first
+ * and the last row that holds a pixel which can write; the rows above the horizon of an indoor frame -- typically
+ * half of the 12.8 MB -- never cross the bus.  Results are identical.  Everything else as above. */
+enum { WSMG_HOST_ZEROCOPY_FEATURES = 1, WSMG_HOST_SKIP_DEAD_ROWS = 2 };
 int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, const float* gps_host,
                             const float* compass_host, const float* mask_host, float* gmap,
                             float* ego_out_host, void* staging, size_t staging_bytes,
@@ -175,6 +179,11 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
 int wsmg_semantic_crop(const float* maps, const float* pose, const float* trig, const int32_t* map_index,
                        int64_t* out, int32_t bs, int32_t n_maps, int32_t S, int32_t half, int32_t origin,
                        void* stream);
+
+/* The host-side test WSMG_HOST_SKIP_DEAD_ROWS applies, exposed for callers and for byte accounting: for every frame of
+ * the HOST depth tensor [bs,Hd,Wd,1], the first and the last sampled feature row holding a pixel that can write
+ * (row_lo[b] > row_hi[b]: none).  Pure host code, no CUDA call. */
+int wsmg_host_live_rows(const float* depth_host, const wsmg_dims* d, int32_t* row_lo, int32_t* row_hi);
 
 #ifdef __cplusplus
 }

@@ -180,6 +180,24 @@ def test_stage_composition_and_host_pipeline():
     pipe0.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)
     torch.cuda.synchronize()
     assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g4, g2)
+    # only the feature rows that hold a pixel which can write cross the bus; the rest of the staging buffer is
+    # poisoned with NaN bit patterns to prove the kernel never looks at it
+    pipe1 = ops.HostPipeline(d, DEV, chunk_envs=2, skip_dead_rows=True)
+    pipe1.staging.fill_(0xFF)
+    g5 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego_h.zero_()
+    pipe1.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g5, ego_h)
+    torch.cuda.synchronize()
+    assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g5, g2)
+    dead = depth.clone()
+    dead[1] = 1.0                                            # 10 m everywhere: this frame copies no feature row at all
+    pipe1.staging.fill_(0xFF)
+    g6 = torch.zeros(bs, 240, 240, c, device=DEV)
+    pipe1.step(feat.pin_memory(), dead.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g6, ego_h)
+    g7 = torch.zeros(bs, 240, 240, c, device=DEV)
+    ego7 = ops.map_update(feat.to(DEV), dead.to(DEV), gps.to(DEV), compass.to(DEV), masks.to(DEV), g7)
+    torch.cuda.synchronize()
+    assert torch.equal(ego_h, ego7.cpu()) and torch.equal(g6, g7)
     from wsmgmap_b200._lib import WsmgError
     with pytest.raises(WsmgError):
         pipe0.step(feat.clone(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)

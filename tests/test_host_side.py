@@ -69,3 +69,27 @@ def test_product_path_has_no_oracle_import():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_live_rows_match_the_oracle():
+    """wsmg_host_live_rows (pure host code of libwsmg.so, what WSMG_HOST_SKIP_DEAD_ROWS copies by) against the rows
+    in which the oracle finds a pixel that can write."""
+    import numpy as np
+    import torch
+    from oracle.mapping_oracle import MapGeometry, spec_cells
+    from wsmgmap_b200 import ops
+    from wsmgmap_b200.synth import make_depth
+    gen = torch.Generator().manual_seed(5)
+    hf, hd = 224, 256
+    depth = torch.cat([make_depth(k, 2, hd, hd, gen) for k in ("room2", "room4", "near", "uniform")], 0)
+    depth[1] = 1.0                                   # nothing can write
+    depth[2, :200] = 0.0                             # holes on top
+    d = ops.dims_for((depth.shape[0], 64, hf, hf), depth.shape, depth.shape[0])
+    lo, hi = ops.host_live_rows(depth, d)
+    _, invalid = spec_cells(depth[..., 0].numpy(), hf, hf, MapGeometry())
+    for b in range(depth.shape[0]):
+        rows = np.nonzero((~invalid[b]).any(axis=1))[0]
+        if rows.size == 0:
+            assert lo[b] > hi[b]
+        else:
+            assert (int(lo[b]), int(hi[b])) == (int(rows[0]), int(rows[-1])), b

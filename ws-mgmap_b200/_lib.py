@@ -42,6 +42,7 @@ SIGNATURES = {
     "wsmg_map_update_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP, _P]),
     "wsmg_semantic_crop": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                           ctypes.c_int32, _P]),
+    "wsmg_host_live_rows": (ctypes.c_int, [_P, _DP, _P, _P]),
     "wsmg_map_update_host_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP,
                                                ctypes.c_uint32, _P]),
 }
@@ -53,6 +54,7 @@ _lib = None
 
 
 HOST_ZEROCOPY_FEATURES = 1   # include/wsmg.h: WSMG_HOST_ZEROCOPY_FEATURES
+HOST_SKIP_DEAD_ROWS = 2      # include/wsmg.h: WSMG_HOST_SKIP_DEAD_ROWS
 
 
 class WsmgError(RuntimeError):

@@ -453,6 +453,26 @@ static size_t slot_bytes(const wsmg_dims* d, int chunk, HostSlot* out, unsigned 
   return off;
 }
 
+// First and last sampled row of one depth frame that holds a pixel which can write (rgb_mapping.py:165-174 evaluated with
+// the device's own arithmetic, wsmg_math.h); lo > hi: none.  A superset test would do -- the kernel only reads
+// the features of pixels that pass exactly this test and land inside the fan.
+static void live_rows_host(const Geo& g, const float* depth_env, const int* col_src, const float* col_xx, int* lo, int* hi) {
+  *lo = g.Hf; *hi = -1;
+  for (int i = 0; i < g.Hf; ++i) {
+    const int r = sample_index(g, i);
+    const float yy = pinhole_yy(g, r);
+    const float* row = depth_env + (size_t)r * g.Wd;
+    for (int j = 0; j < g.Wf; ++j) {
+      int x, y;
+      if (unproject_depth(g, row[col_src[j]], col_xx[j], yy, &x, &y)) {
+        if (i < *lo) *lo = i;
+        *hi = i;
+        break;
+      }
+    }
+  }
+}
+
 size_t wsmg_host_staging_bytes(const wsmg_dims* d, int32_t chunk_envs) {
   if (validate_dims(d) != WSMG_OK || chunk_envs <= 0) return 0;
   int chunk = chunk_envs < d->bs ? chunk_envs : d->bs;
@@ -488,6 +508,14 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
     feat_mapped = static_cast<const float*>(at.devicePointer);
     if (!aligned16(feat_mapped)) return WSMG_E_ALIGN;
   }
+  static_assert(CELLS_MAX_W <= 1024, "column tables live on the stack");
+  int col_src[CELLS_MAX_W];
+  float col_xx[CELLS_MAX_W];
+  if (flags & WSMG_HOST_SKIP_DEAD_ROWS) {
+    if (d->Wf > CELLS_MAX_W) return WSMG_E_DIMS;
+    const Geo g = make_geo(d);
+    for (int j = 0; j < d->Wf; ++j) { col_src[j] = sample_index(g, j); col_xx[j] = pinhole_xx(g, col_src[j]); }
+  }
   cudaStream_t user = (cudaStream_t)stream;
   // two internal streams ping-pong over the two staging slots so that the copies of chunk i+1
   // overlap the kernels of chunk i; both are fenced against the caller's stream with events.
@@ -511,7 +539,23 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
     slot_bytes(d, chunk, &hs, (unsigned char*)staging + slot * one);
     cudaStream_t s = st[slot];
     const size_t fe = (size_t)(d->C_in > 0 ? d->C_in : d->C) * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
-    if (feat_mapped == nullptr) cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
+    if (feat_mapped != nullptr) {
+      // nothing to stage
+    } else if (flags & WSMG_HOST_SKIP_DEAD_ROWS) {
+      const Geo g = make_geo(d);
+      const int planes = d->C_in > 0 ? d->C_in : d->C;
+      const size_t pitch = (size_t)d->Hf * d->Wf * 4;
+      for (int k = 0; k < n; ++k) {
+        int lo, hi;
+        live_rows_host(g, depth_host + (size_t)(b0 + k) * de, col_src, col_xx, &lo, &hi);
+        if (lo > hi) continue;                                   // nothing in this frame can write
+        const size_t first = (size_t)lo * d->Wf;
+        cudaMemcpy2DAsync(hs.feat + (size_t)k * fe + first, pitch, feat_host + (size_t)(b0 + k) * fe + first, pitch,
+                          (size_t)(hi - lo + 1) * d->Wf * 4, planes, cudaMemcpyHostToDevice, s);
+      }
+    } else {
+      cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
+    }
     cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(hs.compass, compass_host + b0, n * 4, cudaMemcpyHostToDevice, s);
@@ -542,6 +586,23 @@ int wsmg_semantic_crop(const float* maps, const float* pose, const float* trig, 
   k_semcrop<<<grid, 256, 0, (cudaStream_t)stream>>>(maps, pose, trig, map_index, reinterpret_cast<long long*>(out), n_maps, S,
                                                      half, origin);
   return (int)cudaGetLastError();
+}
+
+int wsmg_host_live_rows(const float* depth_host, const wsmg_dims* d, int32_t* row_lo, int32_t* row_hi) {
+  int rc = validate_dims(d);
+  if (rc != WSMG_OK) return rc;
+  if (!depth_host || !row_lo || !row_hi) return WSMG_E_NULL;
+  if (d->Wf > CELLS_MAX_W) return WSMG_E_DIMS;
+  const Geo g = make_geo(d);
+  int col_src[CELLS_MAX_W];
+  float col_xx[CELLS_MAX_W];
+  for (int j = 0; j < d->Wf; ++j) { col_src[j] = sample_index(g, j); col_xx[j] = pinhole_xx(g, col_src[j]); }
+  for (int b = 0; b < d->bs; ++b) {
+    int lo, hi;
+    live_rows_host(g, depth_host + (size_t)b * d->Hd * d->Wd, col_src, col_xx, &lo, &hi);
+    row_lo[b] = lo; row_hi[b] = hi;
+  }
+  return WSMG_OK;
 }
 
 }  // extern "C"

@@ -129,13 +129,26 @@ def semantic_crop(maps, pose, half=50, origin=289, trig=None, map_index=None):
     return out
 
 
+def host_live_rows(depth_h, dims):
+    """First / last feature row per frame that holds a pixel which can write (what skip_dead_rows copies); depth_h is
+    the HOST depth tensor [bs,Hd,Wd,1].  Returns two int32 CPU tensors [bs]."""
+    lib = _lib.load()
+    depth_h = depth_h.contiguous()
+    lo = torch.empty(dims.bs, dtype=torch.int32)
+    hi = torch.empty(dims.bs, dtype=torch.int32)
+    _lib.check(lib.wsmg_host_live_rows(_ptr(depth_h), ctypes.byref(dims), _ptr(lo), _ptr(hi)), "wsmg_host_live_rows")
+    return lo, hi
+
+
 class HostPipeline:
     """End-to-end step from HOST (pinned) buffers: H2D of the frame, update, D2H of the ego map,
     chunked so copies overlap the kernels (wsmg_map_update_host_ex).  zero_copy=True: the feature tensor must be
     pinned (`pin_memory()`); the scatter pulls it over the bus itself and skips the pixel groups that cannot write."""
 
-    def __init__(self, dims, device, chunk_envs=32, zero_copy=False):
-        self.flags = _lib.HOST_ZEROCOPY_FEATURES if zero_copy else 0
+    def __init__(self, dims, device, chunk_envs=32, zero_copy=False, skip_dead_rows=False):
+        # skip_dead_rows: the host tests the depth frame first and copies only the feature rows that hold a pixel
+        # which can write (indoor frames: about half)
+        self.flags = (_lib.HOST_ZEROCOPY_FEATURES if zero_copy else 0) | (_lib.HOST_SKIP_DEAD_ROWS if skip_dead_rows else 0)
         self.lib = _lib.load()
         self.dims = dims
         self.device = torch.device(device)
