@@ -11,6 +11,9 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "wsmg_body.h"
 #include "wsmg_host.h"
@@ -453,24 +456,54 @@ static size_t slot_bytes(const wsmg_dims* d, int chunk, HostSlot* out, unsigned 
   return off;
 }
 
-// First and last sampled row of one depth frame that holds a pixel which can write (rgb_mapping.py:165-174 evaluated with
-// the device's own arithmetic, wsmg_math.h); lo > hi: none.  A superset test would do -- the kernel only reads
-// the features of pixels that pass exactly this test and land inside the fan.
+// Does sampled row i of one (host) depth frame hold a pixel that can write?  rgb_mapping.py:165-174 evaluated with the
+// device's own arithmetic (wsmg_math.h).
+static bool row_can_write(const Geo& g, const float* depth_env, const int* col_src, const float* col_xx, int i) {
+  const int r = sample_index(g, i);
+  const float yy = pinhole_yy(g, r);
+  const float* row = depth_env + (size_t)r * g.Wd;
+  // cheap conservative filter (one vector pass over the depth row): a pixel can only write if its height
+  // Y = yy * Z lies in (-1.5, 0.1), i.e. if Z is below a per-row bound; rows whose smallest non-zero depth is
+  // already beyond it (everything above the horizon of an indoor frame) are settled without the exact test
+  float zmin = INFINITY;
+  int c = 0;
+#if defined(__SSE2__)
+  {
+    __m128 vmin = _mm_set1_ps(INFINITY);
+    const __m128 inf = _mm_set1_ps(INFINITY), zero = _mm_setzero_ps();
+    for (; c + 4 <= g.Wd; c += 4) {
+      __m128 v = _mm_loadu_ps(row + c);
+      const __m128 nz = _mm_cmpneq_ps(v, zero);                       // (NaN != 0 is true: a NaN stays and loses the min)
+      v = _mm_or_ps(_mm_and_ps(nz, v), _mm_andnot_ps(nz, inf));
+      vmin = _mm_min_ps(v, vmin);                                     // v < vmin ? v : vmin
+    }
+    float lane[4];
+    _mm_storeu_ps(lane, vmin);
+    for (int l = 0; l < 4; ++l) zmin = lane[l] < zmin ? lane[l] : zmin;
+  }
+#endif
+  for (; c < g.Wd; ++c) {
+    const float v = row[c] != 0.0f ? row[c] : INFINITY;
+    zmin = v < zmin ? v : zmin;
+  }
+  const float bound = yy > 0.0f ? 0.1f / yy : (yy < 0.0f ? 1.5f / -yy : INFINITY);
+  if (!(zmin * 10.0f < bound * 1.0001f)) return false;
+  for (int j = 0; j < g.Wf; ++j) {
+    int x, y;
+    if (unproject_depth(g, row[col_src[j]], col_xx[j], yy, &x, &y)) return true;
+  }
+  return false;
+}
+
+// First and last such row (lo > hi: none), scanning inwards from both ends.  A superset would do -- the kernel only
+// reads the features of pixels that pass exactly this test and land inside the fan.
 static void live_rows_host(const Geo& g, const float* depth_env, const int* col_src, const float* col_xx, int* lo, int* hi) {
   *lo = g.Hf; *hi = -1;
-  for (int i = 0; i < g.Hf; ++i) {
-    const int r = sample_index(g, i);
-    const float yy = pinhole_yy(g, r);
-    const float* row = depth_env + (size_t)r * g.Wd;
-    for (int j = 0; j < g.Wf; ++j) {
-      int x, y;
-      if (unproject_depth(g, row[col_src[j]], col_xx[j], yy, &x, &y)) {
-        if (i < *lo) *lo = i;
-        *hi = i;
-        break;
-      }
-    }
-  }
+  for (int i = 0; i < g.Hf; ++i)
+    if (row_can_write(g, depth_env, col_src, col_xx, i)) { *lo = i; break; }
+  if (*lo == g.Hf) return;
+  for (int i = g.Hf - 1; i >= *lo; --i)
+    if (row_can_write(g, depth_env, col_src, col_xx, i)) { *hi = i; break; }
 }
 
 size_t wsmg_host_staging_bytes(const wsmg_dims* d, int32_t chunk_envs) {
