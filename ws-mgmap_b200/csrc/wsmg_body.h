@@ -450,10 +450,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   for (int t = tid; t < E; t += NT) { I2 e; e.a = E; e.b = -1; ext[t] = e; }     // empty extent
   for (int t = tid; t < E; t += NT) hitrow[t] = p.row_bounds != nullptr ? p.row_bounds[(size_t)b * E + t] : (E << 16);
   for (int t = tid; t < (WSMG_SKIP(2048) ? 0 : SLAB * npp); t += NT) Pk[t] = KEY_EMPTY;
-  WSMG_SYNC();
+  // (the barrier that publishes these tables and the empty key planes sits inside the scatter, after its first
+  // code fetches and feature copies have been issued: their L2 / DRAM latency overlaps the prologue)
 
   // ---- phase 1: scatter-max into the packed fan (rgb_mapping.py:210-225) -----------------------
-  if (p.proj_in == nullptr && !WSMG_SKIP(1)) {
+  const bool do_scatter = p.proj_in == nullptr && !WSMG_SKIP(1);
+  if (!do_scatter) WSMG_SYNC();
+  if (do_scatter) {
     const uint2* codes4 = reinterpret_cast<const uint2*>(p.codes + (size_t)b * HW);
     // Channel pool (rgb_mapping.py:81-84) fused: when Cin != C the scatter runs once per input plane of a bin,
     // all passes reducing into the same key plane (max over channels commutes with the max-scatter).
@@ -511,6 +514,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     for (int s_ = 0; s_ < QD; ++s_) cq[s_] = fetch_codes(t_head + s_ * NT);
 #pragma unroll
     for (int s_ = 0; s_ < STAGES; ++s_) issue(s_, t_head + s_ * NT, cq[s_]);
+    if (pass == 0) WSMG_SYNC();                                // key planes are empty: the first atomic may go
     // unrolled by lcm(QD, STAGES): the code queue's rotation and the slot index turn into register renaming and
     // immediates (measured: -3 % kernel time over the rolled loop; unroll 2 or a shorter / longer queue are slower)
     constexpr int UNR = QD * STAGES;
