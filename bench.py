@@ -163,6 +163,38 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the e2e leg are
+    first-touched in that node's memory (what a production launcher does with numactl).  Best effort; returns the node."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def workload_config(args, world):
     total = 1024 if args.workload == "sweep1024" else 8
     if args.envs:
@@ -186,6 +218,7 @@ def run_native(args, rank, local_rank, world):
         raise RuntimeError("bench.py --impl native needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -371,6 +404,7 @@ def run_native(args, rank, local_rank, world):
             "e2e": {"value": ne * world * Ke / (max_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "envs_per_gpu": ne, "steps": Ke,
                     "api": "wsmg_map_update_host_ex (pinned host buffers, chunked H2D/compute/D2H)", "mode": args.e2e_mode,
+                    "numa_node_rank0": numa_node,
                     "h2d_bytes_per_step_dense": ne * 4 * (s["C"] * s["Hf"] * s["Wf"] + s["Hd"] * s["Wd"] + 4) * world},
             "gpu_launches": 3 * K * world,
             "clocks": clk.summary(),
