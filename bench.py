@@ -153,7 +153,7 @@ def run_reference(args, rank, world):
     sample = f"{n} envs/step x {args.steps} steps of the {args.workload} workload (mixed depth kinds), torch CPU"
     line = {
         "metric": "map-update frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": workload_config(args, world),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
@@ -196,14 +196,21 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 def workload_config(args, world):
-    total = 1024 if args.workload == "sweep1024" else 8
+    """sweep1024 / env8: 1024 / 8 envs PER GPU by default (weak scaling -- every rank owns its envs and their map state,
+    exactly like a rank of the reference owns its NUM_PROCESSES envs); --scaling strong keeps the total fixed and
+    shards it, the literal reading of BASELINE.json configs[3]."""
+    base = 1024 if args.workload == "sweep1024" else 8
     if args.envs:
-        total = args.envs
-    return {"workload": f"{args.workload}: {total} envs total, {total // world} per GPU, env-sharded, "
+        base = args.envs
+    if args.scaling == "weak":
+        per_gpu, total = base, base * world
+    else:
+        per_gpu, total = base // world, base
+    return {"workload": f"{args.workload}: {per_gpu} envs per GPU, {total} in total ({args.scaling} scaling), env-sharded, "
                         f"C={SHAPE['C']} feat {SHAPE['Hf']}x{SHAPE['Wf']} depth {SHAPE['Hd']}x{SHAPE['Wd']} ego 100 global 240 fp32, depth kinds mixed "
                         f"{'/'.join(DEPTH_KINDS)}, random-walk poses, a new frame per env per step, masks=1 after the first step",
-            "envs_total": total, "envs_per_gpu": total // world,
-            "l2": "inputs larger than L2 (no flush)" if total // world >= 64 else "L2 flushed between steps",
+            "envs_total": total, "envs_per_gpu": per_gpu,
+            "l2": "inputs larger than L2 (no flush)" if per_gpu >= 64 else "L2 flushed between steps",
             "bytes_per_frame_algorithmic": algorithmic_bytes_per_frame()}
 
 
@@ -395,7 +402,7 @@ def run_native(args, rank, local_rank, world):
         traffic = args.traffic if args.traffic is not None else (tr_env * n if tr_env is not None else None)
         line = {
             "metric": "map-update frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "strong",
+            "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "native", "config": cfg,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_fused", "kernel_ms": max_fused,
@@ -430,7 +437,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="sweep1024", choices=["sweep1024", "env8"])
-    ap.add_argument("--envs", type=int, default=0, help="override the total env count")
+    ap.add_argument("--envs", type=int, default=0, help="override the env count (per GPU when weak, total when strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's envs per GPU (default); strong: that many in total, sharded")
     ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU in the host-buffer (e2e) leg")
     ap.add_argument("--e2e-chunk", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
