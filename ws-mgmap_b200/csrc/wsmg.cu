@@ -286,7 +286,6 @@ static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
     int rc = encode_window_map(&p.tmap, p.gmap, n_maps, p.g);
     if (rc != 0) return rc;
   }
-  p.use_tma = tma ? 1 : 0;
   if (p.g.Cin != p.g.C) {                                   // channel pool fused in the scatter: run-time geometry builds
     if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s);
     return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s);

@@ -114,8 +114,7 @@ struct TensorMapBlob { unsigned char bytes[8]; };
 #endif
 
 struct FusedParams {
-  TensorMapBlob tmap;       // [n_maps,G,G,C] fp32, box {4, E+2, 1, 1}; valid when use_tma
-  int use_tma;
+  TensorMapBlob tmap;       // [n_maps,G,G,C] fp32, box {4, WWP, TMA_ROWS, 1}; filled for the TMA builds
   const uint32_t* env_flags; // [bs] bit0: the env has at least one pixel that does not write (k_cells)
   const float* feat;        // [bs,C,Hf,Wf]
   const uint16_t* codes;    // [bs,Hf*Wf] packed fan codes from k_cells
@@ -142,10 +141,6 @@ struct FusedParams {
 __device__ __forceinline__ void smem_max(int32_t* a, int32_t v) { atomicMax(a, v); }
 // true when no active lane of the (converged) warp has the sign bit set in `bits`
 __device__ __forceinline__ bool warp_all_nonneg(int32_t bits) { return __ballot_sync(__activemask(), bits < 0) == 0u; }
-__device__ __forceinline__ F4 ld_stream4(const float* p) {
-  float4 t = __ldcs(reinterpret_cast<const float4*>(p));
-  F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
-}
 __device__ __forceinline__ uint2 ld_codes(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void async_copy16(void* dst_smem, const void* src, bool pred) {
@@ -187,7 +182,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #else
 inline void smem_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
 inline bool warp_all_nonneg(int32_t bits) { return bits >= 0; }
-inline F4 ld_stream4(const float* p) { F4 r; for (int i = 0; i < 4; ++i) r.v[i] = p[i]; return r; }
 inline uint2 ld_codes(const uint2* p) { return *p; }
 inline void st_stream(float* p, float v) { *p = v; }
 inline void async_copy16(void* dst, const void* src, bool pred) {
