@@ -338,3 +338,34 @@ def test_window_touching_the_map_border():
     ego2 = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), ones.to(DEV), gmap,
                           trig=_trig(compass).to(DEV))
     assert torch.equal(gmap, before) and torch.equal(ego2.cpu(), want)
+
+
+def test_random_small_geometries_vs_spec():
+    """A dozen random geometries (ego sizes around the band size, odd sizes, maps barely larger than the ego grid,
+    channel counts around the slab size, windows over the map border) through the run-time-geometry kernels,
+    bit-exact against the elementwise spec."""
+    from oracle.mapping_oracle import spec_step
+    rng = np.random.default_rng(2024)
+    for case in range(12):
+        e = int(rng.integers(6, 64)); gl = e + int(rng.integers(0, 60)); c = int(rng.integers(1, 10))
+        hf = 4 * int(rng.integers(2, 11)); hd = int(round(hf * float(rng.choice([1.0, 1.25, 2.0])))); res = 0.2
+        geo = MapGeometry(resolution=res, ego=e, glob=gl)
+        gen = torch.Generator().manual_seed(case)
+        bs = 2
+        gmap = torch.zeros(bs, gl, gl, c, device=DEV)
+        g_spec = np.zeros((bs, gl, gl, c), np.float32)
+        span = gl * res / 2
+        for t in range(2):
+            gps = torch.from_numpy(rng.uniform(-1.2 * span, 1.2 * span, size=(bs, 2)).astype(np.float32))
+            compass = torch.from_numpy(rng.uniform(-np.pi, np.pi, size=(bs, 1)).astype(np.float32))
+            masks = torch.from_numpy((rng.uniform(size=(bs, 1)) > 0.3).astype(np.float32)) if t else torch.zeros(bs, 1)
+            feat = make_features(bs, c, hf, hf, gen, signed=bool(case & 1))
+            depth = make_depth(("near", "room2")[t], bs, hd, hd, gen) * (e * res / 12.0)
+            trig = _trig(compass)
+            ego = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), masks.to(DEV), gmap, e=e,
+                                 resolution=res, trig=trig.to(DEV))
+            tr = trig.numpy()
+            sego, _ = spec_step(g_spec, feat.numpy(), depth[..., 0].numpy(), gps.numpy(), compass.numpy(), masks[:, 0].numpy(),
+                                dict(neg=(tr[:, 0], tr[:, 1]), pos=(tr[:, 2], tr[:, 3])), geo)
+            assert np.array_equal(ego.cpu().numpy(), sego), (case, e, gl, c, hf, hd, t)
+            assert np.array_equal(gmap.cpu().numpy(), g_spec), (case, e, gl, c, hf, hd, t)

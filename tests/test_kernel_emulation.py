@@ -241,3 +241,40 @@ def test_first_rotation_column_bounds_cut_nothing(e, gl):
         assert np.array_equal(gmap[0], fused), a
         back = spec_translate(np.ascontiguousarray(fused.transpose(2, 0, 1)), -tx, -ty)
         assert np.array_equal(ego[0], spec_rotate(back[:, lo:hi, lo:hi], t["pos"][0][0], t["pos"][1][0])), a
+
+
+def test_random_small_geometries_match_spec():
+    """Property test over geometry: ego sizes below, at and above the band size, odd sizes, global maps barely larger
+    than the ego grid, channel counts around the slab size, poses that push the window over the map border --
+    the emulated CTA body (run-time geometry build) against the elementwise spec, two steps each."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=80, deadline=None)
+    @given(e=st.integers(6, 64), extra=st.integers(0, 60), c=st.integers(1, 9), hq=st.integers(2, 10),
+           kd=st.sampled_from([1.0, 1.25, 2.0]), seed=st.integers(0, 10_000))
+    def run(e, extra, c, hq, kd, seed):
+        gl = e + extra
+        hf = 4 * hq                                   # Hf*Wf must be a multiple of 4
+        hd = int(round(hf * kd))
+        res = 0.2
+        geo = MapGeometry(resolution=res, ego=e, glob=gl)
+        rng = np.random.default_rng(seed)
+        gen = torch.Generator().manual_seed(seed)
+        bs = 2
+        g_emul = np.zeros((bs, gl, gl, c), np.float32)
+        g_spec = np.zeros((bs, gl, gl, c), np.float32)
+        span = gl * res / 2
+        for t in range(2):
+            gps = rng.uniform(-1.2 * span, 1.2 * span, size=(bs, 2)).astype(np.float32)
+            compass = rng.uniform(-np.pi, np.pi, size=(bs, 1)).astype(np.float32)
+            masks = (rng.uniform(size=(bs, 1)) > 0.3).astype(np.float32) if t else np.zeros((bs, 1), np.float32)
+            feat = make_features(bs, c, hf, hf, gen, signed=bool(seed & 1)).numpy()
+            depth = (make_depth(("near", "room2")[t], bs, hd, hd, gen)[..., 0].numpy() * (e * res / 12.0)).astype(np.float32)
+            trig = _trig(torch.from_numpy(compass))
+            ego, proj = emul_step(g_emul, feat, depth, gps, compass, masks, trig=trig, want_proj=True, e=e, g=gl, res=res)
+            sego, inter = spec_step(g_spec, feat, depth, gps, compass, masks[:, 0], _trig_dict(trig), geo)
+            assert np.array_equal(proj, inter["proj"])
+            assert np.array_equal(ego, sego)
+            assert np.array_equal(g_emul, g_spec)
+
+    run()
