@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
 // neighbour subsampling (rgb_mapping.py:188-196) then gathers from shared memory.  Also emits the
 // reference-shaped (linear index, invalid) pair for the stage API and the per-env "some pixel does not
 // write" flag (those pixels send the sentinel to cell 0, rgb_mapping.py:207-212).
-constexpr int CELLS_PX = 4;
+constexpr int CELLS_PX = 4;             // pixels per packed code word
+constexpr int CELLS_GROUPS = 2;         // code words per thread: the per-block tables are built once per 2048 pixels
 constexpr int CELLS_MAX_W = 1024;
 // STAGE_API: also write the reference-shaped (lin, invalid) arrays (stage entry point only; the step never does).
 template <bool STAGE_API>
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   float* drows = reinterpret_cast<float*>(cells_smem);       // [stage_rows][Wd] when stage_rows > 0
   const int b = blockIdx.y;
   const int HW = g.Hf * g.Wf;
-  const int per_block = CELLS_THREADS * CELLS_PX;
+  const int per_block = CELLS_THREADS * CELLS_PX * CELLS_GROUPS;
   const int t_first = blockIdx.x * per_block;
   const int t_last = (t_first + per_block < HW ? t_first + per_block : HW) - 1;
   const float* depth_b = depth + (size_t)b * g.Hd * g.Wd;
@@ -114,54 +115,57 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   }
   __syncthreads();
   if (staged) mbar_wait(&bar, 0);
-  const int t0 = t_first + threadIdx.x * CELLS_PX;
-  int i = t0 / g.Wf, j = t0 - i * g.Wf;
-  int r = sample_index(g, i);
-  float yy = pinhole_yy(g, r);
-  uint32_t code[CELLS_PX];
   bool any_bad = false, any_outlier = false;
-  auto one_pixel = [&](int px, int t, float dval, float xx) {
-    int x, y;
-    const bool ok = unproject_depth(g, dval, xx, yy, &x, &y);
-    any_bad |= !ok;
-    code[px] = CODE_INVALID;
-    if (ok) {
-      if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
-      else { code[px] = CODE_OUTLIER; any_outlier = true; }
-    }
-    if (STAGE_API) {
-      if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
-      if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
-    }
-  };
-  if ((g.Wf & 3) == 0 && t0 + CELLS_PX <= HW) {
-    // the four pixels share a row: one row pointer, the column tables as two 16-byte reads
-    const int4 cs = *reinterpret_cast<const int4*>(&col_src[j]);
-    const float4 cx = *reinterpret_cast<const float4*>(&col_xx[j]);
-    float d0, d1, d2, d3;
-    if (staged) {                                            // (kept apart so that the staged reads are LDS, not generic loads)
-      const float* row = drows + (r - r_first) * g.Wd;
-      d0 = row[cs.x]; d1 = row[cs.y]; d2 = row[cs.z]; d3 = row[cs.w];
-    } else {
-      const float* row = depth_b + (size_t)r * g.Wd;
-      d0 = __ldg(row + cs.x); d1 = __ldg(row + cs.y); d2 = __ldg(row + cs.z); d3 = __ldg(row + cs.w);
-    }
-    one_pixel(0, t0, d0, cx.x); one_pixel(1, t0 + 1, d1, cx.y); one_pixel(2, t0 + 2, d2, cx.z); one_pixel(3, t0 + 3, d3, cx.w);
-  } else {
 #pragma unroll
-    for (int px = 0; px < CELLS_PX; ++px) {
-      const int t = t0 + px;
+  for (int grp = 0; grp < CELLS_GROUPS; ++grp) {
+    const int t0 = t_first + (grp * CELLS_THREADS + threadIdx.x) * CELLS_PX;   // a warp's words stay consecutive
+    int i = t0 / g.Wf, j = t0 - i * g.Wf;
+    int r = sample_index(g, i);
+    float yy = pinhole_yy(g, r);
+    uint32_t code[CELLS_PX];
+    auto one_pixel = [&](int px, int t, float dval, float xx) {
+      int x, y;
+      const bool ok = unproject_depth(g, dval, xx, yy, &x, &y);
+      any_bad |= !ok;
       code[px] = CODE_INVALID;
-      if (t < HW) {
-        const float dval = staged ? drows[(r - r_first) * g.Wd + col_src[j]] : depth_b[(size_t)r * g.Wd + col_src[j]];
-        one_pixel(px, t, dval, col_xx[j]);
-        if (++j == g.Wf) { j = 0; ++i; r = sample_index(g, i); yy = pinhole_yy(g, r); }
+      if (ok) {
+        if (y < g.fan_rows && x >= fan_x_lo(y) && x <= fan_x_hi(y, g.E)) code[px] = (uint32_t)(rowoff[y] + x - fan_x_lo(y));
+        else { code[px] = CODE_OUTLIER; any_outlier = true; }
+      }
+      if (STAGE_API) {
+        if (lin != nullptr) lin[(size_t)b * HW + t] = y * g.E + x;
+        if (invalid != nullptr) invalid[(size_t)b * HW + t] = ok ? 0 : 1;
+      }
+    };
+    if ((g.Wf & 3) == 0 && t0 + CELLS_PX <= HW) {
+      // the four pixels share a row: one row pointer, the column tables as two 16-byte reads
+      const int4 cs = *reinterpret_cast<const int4*>(&col_src[j]);
+      const float4 cx = *reinterpret_cast<const float4*>(&col_xx[j]);
+      float d0, d1, d2, d3;
+      if (staged) {                                            // (kept apart so that the staged reads are LDS, not generic loads)
+        const float* row = drows + (r - r_first) * g.Wd;
+        d0 = row[cs.x]; d1 = row[cs.y]; d2 = row[cs.z]; d3 = row[cs.w];
+      } else {
+        const float* row = depth_b + (size_t)r * g.Wd;
+        d0 = __ldg(row + cs.x); d1 = __ldg(row + cs.y); d2 = __ldg(row + cs.z); d3 = __ldg(row + cs.w);
+      }
+      one_pixel(0, t0, d0, cx.x); one_pixel(1, t0 + 1, d1, cx.y); one_pixel(2, t0 + 2, d2, cx.z); one_pixel(3, t0 + 3, d3, cx.w);
+    } else {
+  #pragma unroll
+      for (int px = 0; px < CELLS_PX; ++px) {
+        const int t = t0 + px;
+        code[px] = CODE_INVALID;
+        if (t < HW) {
+          const float dval = staged ? drows[(r - r_first) * g.Wd + col_src[j]] : depth_b[(size_t)r * g.Wd + col_src[j]];
+          one_pixel(px, t, dval, col_xx[j]);
+          if (++j == g.Wf) { j = 0; ++i; r = sample_index(g, i); yy = pinhole_yy(g, r); }
+        }
       }
     }
-  }
-  if (codes != nullptr && t0 < HW) {       // HW % 4 == 0 (validated): the four codes are one aligned 8-byte word
-    uint2 w; w.x = code[0] | (code[1] << 16); w.y = code[2] | (code[3] << 16);
-    *reinterpret_cast<uint2*>(codes + (size_t)b * HW + t0) = w;
+    if (codes != nullptr && t0 < HW) {       // HW % 4 == 0 (validated): the four codes are one aligned 8-byte word
+      uint2 w; w.x = code[0] | (code[1] << 16); w.y = code[2] | (code[3] << 16);
+      *reinterpret_cast<uint2*>(codes + (size_t)b * HW + t0) = w;
+    }
   }
   const unsigned bad = __ballot_sync(0xFFFFFFFFu, any_bad);
   const unsigned outl = __ballot_sync(0xFFFFFFFFu, any_outlier);
@@ -214,7 +218,7 @@ static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8
                         const Geo& g, int bs, cudaStream_t s) {
   if (g.fan_rows > 160 || g.Wf > CELLS_MAX_W) return WSMG_E_DIMS;
   const int HW = g.Hf * g.Wf;
-  const int per_block = CELLS_THREADS * CELLS_PX;
+  const int per_block = CELLS_THREADS * CELLS_PX * CELLS_GROUPS;
   dim3 grid((HW + per_block - 1) / per_block, bs);
   // depth rows one block can touch: its sampled rows (per_block / Wf + 2) times the subsampling ratio, + 1
   int stage_rows = (int)((per_block / g.Wf + 2) * (double)g.Hd / g.Hf) + 2;
