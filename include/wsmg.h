@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WSMG_ABI_VERSION 2
+#define WSMG_ABI_VERSION 3
 
 enum {
   WSMG_OK = 0,
@@ -59,7 +59,14 @@ typedef struct wsmg_dims {
 int wsmg_abi_version(void);
 const char* wsmg_error_string(int code);
 
-/* Bytes of device scratch wsmg_map_update needs for `d` (packed cell codes + flags). */
+/* Test / profiling hook, the library's only process-wide state: which build of k_fused serves the reference shapes.
+ * force_generic = 1: the run-time-geometry kernel instead of the compile-time one; no_tma = 1: the map window moves
+ * with cp.async / st.global instead of TMA.  Results are bit-identical (tests/test_gpu_parity.py compares all four).
+ * Negative arguments return to the default: the environment variables WSMG_FORCE_GENERIC / WSMG_NO_TMA, read once. */
+void wsmg_debug_switches(int force_generic, int no_tma);
+
+/* Bytes of device scratch wsmg_map_update needs for `d`: packed cell codes, per-env flags and rotation tables, and one
+ * crop slot (E*E*16 bytes) per resident k_fused CTA -- at most 320 slots (51 MB at E = 100), independent of bs beyond that. */
 size_t wsmg_scratch_bytes(const wsmg_dims* d);
 
 /* Per-env status words the update leaves in scratch (uint32 each, at byte offset wsmg_scratch_flags_offset(d)):
@@ -67,9 +74,13 @@ size_t wsmg_scratch_bytes(const wsmg_dims* d);
  *   WSMG_FLAG_OUTSIDE_FAN    a *valid* pixel fell outside the packed fan the scatter keeps in shared memory.
  *                            Only depth < 0 can do that (Habitat depth is in [0,1]); such pixels are DROPPED,
  *                            which the reference would not do -- callers that cannot rule them out should check
- *                            this bit (the Python module raises when `strict_inputs` is set). */
+ *                            this bit (the Python module raises when `strict_inputs` is set).
+ *   WSMG_FLAG_BAD_SLOT       wsmg_opts.env_slots[b] is not a row of the map tensor (>= n_maps or negative): the
+ *                            frame was SKIPPED (map untouched, ego row not written).
+ * wsmg_opts.status (optional) receives the same two problem bits without a device synchronisation. */
 #define WSMG_FLAG_INVALID_PIXEL 1u
 #define WSMG_FLAG_OUTSIDE_FAN 2u
+#define WSMG_FLAG_BAD_SLOT 4u
 size_t wsmg_scratch_flags_offset(const wsmg_dims* d);
 
 /* Whole step: Mapping.project_feat_to_map (rgb_mapping.py:32-72) as called by
@@ -94,27 +105,26 @@ int wsmg_map_update(const float* feat, const float* depth, const float* gps, con
  *   env_slots   [bs] int32: frame b reads / updates map row env_slots[b] (< n_maps) instead of row b, so
  *               pausing finished envs is an index-table edit instead of the reference's
  *               full_global_map[state_index] re-materialisation (common_trainer.py:171-172,454-476).
- *               Slots must be distinct.
- *   ev_before_fused / ev_after_fused   cudaEvent_t recorded around the k_fused launch (profiling). */
+ *               Slots must be distinct (two frames on one row race); a slot outside [0, n_maps) skips its frame
+ *               and raises WSMG_FLAG_BAD_SLOT.
+ *   ev_before_fused / ev_after_fused   cudaEvent_t recorded around the k_fused launch (profiling; bench.py times
+ *               the dominant kernel with them).
+ *   status      device-ACCESSIBLE uint32[2] the kernels raise without any synchronisation -- meant to be pinned,
+ *               mapped host memory (cudaHostAlloc / torch pin_memory) that the caller polls from the CPU at its
+ *               next call: status[0] != 0: a valid pixel fell outside the fan and was dropped (WSMG_FLAG_OUTSIDE_FAN);
+ *               status[1] != 0: an env slot was out of range (WSMG_FLAG_BAD_SLOT).  Sticky until the caller clears it. */
 typedef struct wsmg_opts {
   const float* trig;
   void* ego_half;
   const int32_t* env_slots;
   void* ev_before_fused;
   void* ev_after_fused;
+  uint32_t* status;
 } wsmg_opts;
 
 int wsmg_map_update_ex(const float* feat, const float* depth, const float* gps, const float* compass,
                        const float* mask, float* gmap, float* ego_out, const wsmg_opts* opts,
                        void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream);
-
-/* wsmg_map_update, additionally recording two CUDA events (cudaEvent_t passed as void*, either may
- * be NULL) on `stream` immediately before and after the k_fused launch.  bench.py uses it to time the
- * dominant kernel live for the roofline; results are identical to wsmg_map_update. */
-int wsmg_map_update_timed(const float* feat, const float* depth, const float* gps, const float* compass,
-                          const float* mask, float* gmap, float* ego_out, const float* trig,
-                          void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream,
-                          void* ev_before_fused, void* ev_after_fused);
 
 /* Stage: ComputeSpatialLocs.forward + the index half of ProjectToGroundPlane.forward
  * (rgb_mapping.py:153-176, 188-217).  Outputs per sampled pixel of the Hf x Wf frame:
@@ -131,10 +141,11 @@ int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out,
 
 /* Stage: everything after the projection (rgb_mapping.py:35, 37(rotate via :267), 40-70):
  * rotate(-compass), paste, translate, mask + max-fuse into gmap, translate back, crop, rotate(+compass).
- *   proj_in  [bs,C,E,E] fp32 NCHW = proj_feats. */
+ *   proj_in  [bs,C,E,E] fp32 NCHW = proj_feats, zero outside the fan a depth >= 0 pixel can reach (what
+ *            wsmg_scatter_max produces; other cells are ignored).  scratch as for wsmg_map_update. */
 int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const float* compass,
                                 const float* mask, float* gmap, float* ego_out, const float* trig,
-                                const wsmg_dims* d, void* stream);
+                                void* scratch, size_t scratch_bytes, const wsmg_dims* d, void* stream);
 
 /* Host helper: ATen's affine_grid base coordinates, linspace(-1,1,n)*(n-1)/n (align_corners=False),
  * as torch-CPU produces them.  Used by tests to pin the in-kernel tables. */

@@ -1,9 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference file by path.
 
-Only usable where /root/reference exists (the build container).  It never
-travels to the GPU box; what travels are the golden vectors generated from it
-(tests/golden/, made by oracle/make_golden.py) and the restatement in
-oracle/mapping_oracle.py which is asserted equal to it here.
+The file is read from /root/reference in the build container, else from the
+verbatim copy __graft_entry__.build() leaves under baseline/_ref/ (git-ignored,
+never committed; gpurun ships it to the GPU box so that bench.py's reference arm
+and the policy drop-in test can execute the reference's own code there).  The
+golden vectors generated from it (tests/golden/, made by oracle/make_golden.py)
+and the restatement in oracle/mapping_oracle.py, asserted equal to it here, pin
+parity independently of that copy.
 
 The reference module (vlnce_baselines/common/rgb_mapping.py) needs two shims
 to execute without Habitat / torch_scatter / a GPU:
@@ -21,7 +24,22 @@ import types
 
 import torch
 
-REFERENCE_FILE = "/root/reference/vlnce_baselines/common/rgb_mapping.py"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Where the unmodified reference lives: the read-only checkout in the build container, else the copy that
+# __graft_entry__.build() places under baseline/_ref/ (git-ignored, shipped to the GPU box by gpurun).
+REFERENCE_ROOTS = ("/root/reference", os.path.join(_ROOT, "baseline", "_ref"))
+
+
+def reference_path(rel: str):
+    """Absolute path of reference file `rel` (e.g. 'vlnce_baselines/common/rgb_mapping.py'), or None."""
+    for root in REFERENCE_ROOTS:
+        p = os.path.join(root, rel)
+        if os.path.isfile(p):
+            return p
+    return None
+
+
+REFERENCE_FILE = reference_path("vlnce_baselines/common/rgb_mapping.py") or "/root/reference/vlnce_baselines/common/rgb_mapping.py"
 
 
 def reference_available() -> bool:
@@ -34,12 +52,12 @@ def _scatter_max(src, index, dim=-1, out=None, dim_size=None):
     shape = list(src.shape)
     shape[dim] = int(dim_size)
     lowest = torch.finfo(src.dtype).min
-    res = torch.full(shape, lowest, dtype=src.dtype)
+    res = torch.full(shape, lowest, dtype=src.dtype, device=src.device)
     res.scatter_reduce_(dim, index, src, reduce="amax", include_self=True)
-    cnt = torch.zeros(shape, dtype=torch.int32)
+    cnt = torch.zeros(shape, dtype=torch.int32, device=src.device)
     cnt.scatter_add_(dim, index, torch.ones_like(index, dtype=torch.int32))
     res = torch.where(cnt > 0, res, torch.zeros_like(res))
-    arg = torch.full(shape, src.size(dim), dtype=torch.long)
+    arg = torch.full(shape, src.size(dim), dtype=torch.long, device=src.device)
     return res, arg
 
 
@@ -68,18 +86,14 @@ def load_reference_module():
     return mod
 
 
-def make_reference_mapper(num_proc, **kw):
-    """Instantiate the reference RGBMapping on CPU."""
+def make_reference_mapper(num_proc, device="cpu", **kw):
+    """Instantiate the reference RGBMapping.  device="cpu": the hard-coded torch.device("cuda", id) of
+    rgb_mapping.py:14 is redirected to the CPU while the constructor runs; device="cuda": the file runs as it
+    is on cuda:gpu_id (the stock-PyTorch comparator on the GPU box)."""
     mod = load_reference_module()
+    if torch.device(device).type == "cuda":
+        return mod.RGBMapping(_Cfg(num_proc, gpu_id=torch.device(device).index or 0, **kw)), mod
     real_device = torch.device
-
-    class _DevShim:
-        def __call__(self, *a, **k):
-            return real_device("cpu")
-
-        def __instancecheck__(self, obj):
-            return isinstance(obj, real_device)
-
     orig = mod.torch.device
     try:
         mod.torch.device = lambda *a, **k: real_device("cpu")
@@ -90,7 +104,7 @@ def make_reference_mapper(num_proc, **kw):
 
 
 # ------------------------------------------------------------------ the ground-truth semantic map sensor
-SENSOR_FILE = "/root/reference/habitat_extensions/sensors.py"
+SENSOR_FILE = reference_path("habitat_extensions/sensors.py") or "/root/reference/habitat_extensions/sensors.py"
 
 
 def sensor_reference_available() -> bool:

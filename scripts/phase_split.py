@@ -47,7 +47,9 @@ for mask, name in ((1, "scatter"), (2, "first rotation"), (4, "band loop (incl. 
                    (15 + 2048, "all four + key-plane init"), (15 + 512 + 1024 + 2048, "all four + decode + tables + init"),
                    (16384, "scatter: the shared-memory atomics only"), (32768, "scatter: the feature copies only (cp.async)"),
                    (16384 + 32768, "scatter: atomics + copies (codes, staging reads, run merging remain)"),
-                   (4096, "everything: CTAs return at entry (k_reset + k_cells + launch cost)")):
+                   (65536, "output rotation: the B tile copies only (cp.async from the crop slot)"),
+                   (8 + 65536, "output rotation incl. its tile copies"),
+                   (4096, "everything: items return at entry (k_reset + k_cells + launch + dispenser cost)")):
     os.environ["WSMG_DEBUG_SKIP"] = str(mask)
     t = timeit(lambda: ops.map_update(feat, depth, gps, compass, ones, gmap, scratch=scratch, ego=ego))
     print(f"  skip {name:34s} -> {t:.3f} ms  (saves {t_full - t:+.3f})")

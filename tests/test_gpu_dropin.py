@@ -95,7 +95,8 @@ def test_channel_rebinning_and_input_checks():
 
 
 def test_optin_extras_env_slots_and_half_store():
-    """slot table instead of map[state_index]; fp16 ego map for the rollout store."""
+    """slot table instead of map[state_index]; fp16 ego map for the rollout store.  Both are
+    checked against the ORACLE stepped the reference's way (re-indexed state), not only against each other."""
     import numpy as np
     c, hf, hd, n = 8, 64, 64, 4
     gen = torch.Generator().manual_seed(3)
@@ -105,26 +106,110 @@ def test_optin_extras_env_slots_and_half_store():
                 torch.randn(bs, 2, generator=gen), torch.rand(bs, 1, generator=gen) * 6 - 3)
 
     a, b = RGBMapping(_cfg(n, c)), RGBMapping(_cfg(n, c))        # a: reference-style re-indexing, b: slot table
+    orc = OracleMapper(n, c)
     b.store_half = True
     feat, depth, gps, compass = frame(n)
     obs = lambda: dict(depth=depth.to(DEV), gps=gps.to(DEV), compass=compass.to(DEV))  # noqa: E731
     oa = a(feat.to(DEV), obs(), torch.zeros(n, 1, device=DEV))
     ob = b(feat.to(DEV), obs(), torch.zeros(n, 1, device=DEV))
+    want = orc.step(feat, depth, gps, compass, torch.zeros(n, 1))
     assert torch.equal(oa, ob)
+    assert _close(ob.cpu(), want, 1.0) and _close(b.full_global_map.cpu(), orc.full_global_map, 1.0)
     host = b.ego_half_to_host()
     torch.cuda.synchronize()
     assert np.array_equal(host.numpy(), oa.cpu().numpy().astype(np.float16))     # common_trainer.py:519-520
+    assert np.allclose(host.numpy().astype(np.float32), want.numpy(), rtol=1e-3, atol=1e-3)   # fp16 of the oracle's map
     keep = [0, 1, 3]
     a.full_global_map = a.full_global_map[keep]                                  # what _pause_envs does
+    orc.full_global_map = orc.full_global_map[keep]
     b.pause_envs([2])
     assert b.env_slots.tolist() == keep and b.full_global_map.shape[0] == n
+    paused_row = b.full_global_map[2].clone()
     feat, depth, gps, compass = frame(3)
     oa = a(feat.to(DEV), obs(), torch.ones(3, 1, device=DEV))
     ob = b(feat.to(DEV), obs(), torch.ones(3, 1, device=DEV))
+    want = orc.step(feat, depth, gps, compass, torch.ones(3, 1))
     assert torch.equal(oa, ob)
     assert torch.equal(a.full_global_map, b.full_global_map[keep])
+    assert _close(ob.cpu(), want, 1.0) and _close(b.full_global_map[keep].cpu(), orc.full_global_map, 1.0)
+    assert torch.equal(b.full_global_map[2], paused_row)                         # the paused env's map is untouched
     b.pause_envs([0])                                                            # slots compose: [1, 3]
     assert b.env_slots.tolist() == [1, 3]
+    feat, depth, gps, compass = frame(2)
+    ob = b(feat.to(DEV), obs(), torch.tensor([[1.0], [0.0]], device=DEV))        # second frame starts a new episode
+    orc.full_global_map = orc.full_global_map[[1, 2]]
+    want = orc.step(feat, depth, gps, compass, torch.tensor([[1.0], [0.0]]))
+    assert _close(ob.cpu(), want, 1.0) and _close(b.full_global_map[[1, 3]].cpu(), orc.full_global_map, 1.0)
+
+
+def test_env_slot_validation_and_rebinding():
+    """a slot table must address distinct, existing rows of the map it was made for; re-binding the map
+    with another leading dimension (what the unmodified trainer does) drops it instead of leaving stale rows."""
+    import ctypes
+    import warnings
+    from wsmgmap_b200 import _lib, ops
+    c, hf, hd, n = 4, 32, 32, 4
+    m = RGBMapping(_cfg(n, c))
+    with pytest.raises(ValueError, match="rows of full_global_map"):
+        m.env_slots = [0, 4]
+    with pytest.raises(ValueError, match="distinct"):
+        m.env_slots = torch.tensor([1, 1], dtype=torch.int32)
+    m.pause_envs([1])
+    assert m.env_slots.tolist() == [0, 2, 3] and m.env_slots.dtype == torch.int32 and m.env_slots.device == DEV
+    gen = torch.Generator().manual_seed(9)
+    feat, depth = make_features(2, c, hf, hf, gen).to(DEV), make_depth("near", 2, hd, hd, gen).to(DEV)
+    obs = dict(depth=depth, gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
+    with pytest.raises(ValueError, match="entries for a batch"):
+        m(feat, dict(obs), torch.ones(2, 1, device=DEV))                         # 3 slots, batch of 2
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m.full_global_map = m.full_global_map[[0, 2, 3]]                         # the trainer re-indexes as well: table dropped
+        assert any("slot table" in str(x.message) for x in w)
+    assert m.env_slots is None
+    # the C ABI on its own: a slot outside the map skips that frame, raises the flag and the status word
+    lib = _lib.load()
+    gmap = torch.zeros(2, 240, 240, c, device=DEV)
+    ego = torch.full((2, c, 100, 100), -7.0, device=DEV)
+    d = ops.dims_for(feat.shape, depth.shape, 2)
+    scratch = ops.alloc_scratch(d, DEV)
+    slots = torch.tensor([1, 5], dtype=torch.int32, device=DEV)
+    status = torch.zeros(2, dtype=torch.int32).pin_memory()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    opts = _lib.WsmgOpts(None, None, P(slots), None, None, P(status))
+    z = torch.zeros(2, 2, device=DEV)
+    rc = lib.wsmg_map_update_ex(P(feat), P(depth), P(z), P(z), P(z), P(gmap), P(ego), ctypes.byref(opts), P(scratch),
+                                scratch.numel(), ctypes.byref(d), None)
+    torch.cuda.synchronize()
+    assert rc == 0 and status[1].item() == 1
+    flags = ops.env_flags(scratch, d)
+    assert (flags[1] & _lib.FLAG_BAD_SLOT) and not (flags[0] & _lib.FLAG_BAD_SLOT)
+    assert (ego[1] == -7.0).all() and not (ego[0] == -7.0).all()                 # frame 1 skipped, frame 0 done (on row 1)
+    assert gmap[1].abs().sum() > 0 and gmap[0].abs().sum() == 0
+
+
+def test_negative_depth_warns_lazily_without_sync():
+    """Default path (strict_inputs off): pixels behind the camera are dropped -- the one documented divergence from
+    the reference -- and the module says so at its next call, from a pinned status word, without synchronising."""
+    import warnings
+    m = RGBMapping(_cfg(2, 4))
+    gen = torch.Generator().manual_seed(4)
+    feat = make_features(2, 4, 32, 32, gen).to(DEV)
+    depth = make_depth("near", 2, 32, 32, gen)
+    depth[1, :16, :, 0] = -0.2
+    obs = dict(depth=depth.to(DEV), gps=torch.zeros(2, 2, device=DEV), compass=torch.zeros(2, 1, device=DEV))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m(feat, dict(obs), torch.zeros(2, 1, device=DEV))
+        torch.cuda.synchronize()                                                 # (only so that the test is deterministic)
+        assert not any("depth < 0" in str(x.message) for x in w)
+        obs2 = dict(depth=depth.clamp_min(0).to(DEV), gps=obs["gps"], compass=obs["compass"])
+        m(feat, obs2, torch.ones(2, 1, device=DEV))
+        assert any("depth < 0" in str(x.message) for x in w)
+        n = len(w)
+        m(feat, dict(obs2), torch.ones(2, 1, device=DEV))                        # reported once, not again
+        torch.cuda.synchronize()
+        m(feat, dict(obs2), torch.ones(2, 1, device=DEV))
+        assert len([x for x in w if "depth < 0" in str(x.message)]) == len([x for x in w[:n] if "depth < 0" in str(x.message)])
 
 
 def test_strict_inputs_flags_negative_depth():

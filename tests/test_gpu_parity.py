@@ -157,14 +157,23 @@ def test_stage_composition_and_host_pipeline():
     gps = torch.randn(bs, 2, generator=gen)
     compass = torch.rand(bs, 1, generator=gen) * 6 - 3
     masks = torch.zeros(bs, 1)
+    orc = OracleMapper(bs, c)
+    want = orc.step(feat, depth, gps, compass, masks)        # every leg below is held against the oracle (device sin / cos: tolerance)
+
+    def close(a, b):
+        return ((a - b).abs() <= 1e-5 * b.abs() + 2e-5).all()
+
     g1 = torch.zeros(bs + 2, 240, 240, c, device=DEV)        # bs < n_maps: rows [bs:] stay untouched
     g1[bs:] = 3.0
     ego1 = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), masks.to(DEV), g1)
     assert (g1[bs:] == 3.0).all()
+    assert close(ego1.cpu(), want) and close(g1[:bs].cpu(), orc.full_global_map)
     proj = ops.scatter_max(feat.to(DEV), depth.to(DEV))
     g2 = torch.zeros(bs, 240, 240, c, device=DEV)
     ego2 = ops.register_fuse_retrieve(proj, gps.to(DEV), compass.to(DEV), masks.to(DEV), g2)
     assert torch.equal(ego1, ego2) and torch.equal(g1[:bs], g2)
+    orc.step(feat, depth, gps, compass, masks, keep=True)    # (masks == 0: the same step again)
+    assert torch.equal(proj.cpu(), orc.last["proj"])         # the stage output itself is bit-exact: no trigonometry involved
     # host-buffer entry (pinned), chunked: same result
     d = ops.dims_for(feat.shape, depth.shape, bs)
     pipe = ops.HostPipeline(d, DEV, chunk_envs=2)
@@ -173,6 +182,7 @@ def test_stage_composition_and_host_pipeline():
     pipe.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g3, ego_h)
     torch.cuda.synchronize()
     assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g3, g2)
+    assert close(ego_h, want) and close(g3.cpu(), orc.full_global_map)
     # zero-copy features: the scatter reads the pinned host tensor itself; pageable memory is refused
     pipe0 = ops.HostPipeline(d, DEV, chunk_envs=3, zero_copy=True)
     g4 = torch.zeros(bs, 240, 240, c, device=DEV)
@@ -180,6 +190,7 @@ def test_stage_composition_and_host_pipeline():
     pipe0.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)
     torch.cuda.synchronize()
     assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g4, g2)
+    assert close(ego_h, want) and close(g4.cpu(), orc.full_global_map)
     # only the feature rows that hold a pixel which can write cross the bus; the rest of the staging buffer is
     # poisoned with NaN bit patterns to prove the kernel never looks at it
     pipe1 = ops.HostPipeline(d, DEV, chunk_envs=2, skip_dead_rows=True)
@@ -189,6 +200,7 @@ def test_stage_composition_and_host_pipeline():
     pipe1.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g5, ego_h)
     torch.cuda.synchronize()
     assert torch.equal(ego_h, ego1.cpu()) and torch.equal(g5, g2)
+    assert close(ego_h, want) and close(g5.cpu(), orc.full_global_map)
     dead = depth.clone()
     dead[1] = 1.0                                            # 10 m everywhere: this frame copies no feature row at all
     pipe1.staging.fill_(0xFF)
@@ -198,6 +210,9 @@ def test_stage_composition_and_host_pipeline():
     ego7 = ops.map_update(feat.to(DEV), dead.to(DEV), gps.to(DEV), compass.to(DEV), masks.to(DEV), g7)
     torch.cuda.synchronize()
     assert torch.equal(ego_h, ego7.cpu()) and torch.equal(g6, g7)
+    orc_dead = OracleMapper(bs, c)
+    want_dead = orc_dead.step(feat, dead, gps, compass, masks)
+    assert close(ego_h, want_dead) and close(g6.cpu(), orc_dead.full_global_map)
     from wsmgmap_b200._lib import WsmgError
     with pytest.raises(WsmgError):
         pipe0.step(feat.clone(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)
@@ -267,18 +282,17 @@ def test_kernel_variants_agree():
         frames.append((make_features(bs, c, hf, hf, gen).to(DEV), make_depth(("room2", "uniform", "near", "room4")[t], bs, hd, hd, gen).to(DEV),
                        gps.to(DEV), compass.to(DEV), masks.to(DEV)))
     results = {}
+    from wsmgmap_b200 import _lib
     try:
         for no_tma in ("0", "1"):
             for generic in ("0", "1"):
-                os.environ["WSMG_NO_TMA"] = no_tma
-                os.environ["WSMG_FORCE_GENERIC"] = generic
+                _lib.load().wsmg_debug_switches(int(generic), int(no_tma))
                 gmap = torch.zeros(bs, 240, 240, c, device=DEV)
                 egos = [ops.map_update(f, d, g, cp, m, gmap).clone() for f, d, g, cp, m in frames]
                 torch.cuda.synchronize()
                 results[(no_tma, generic)] = (egos, gmap)
     finally:
-        os.environ.pop("WSMG_NO_TMA", None)
-        os.environ.pop("WSMG_FORCE_GENERIC", None)
+        _lib.load().wsmg_debug_switches(-1, -1)
     ref_egos, ref_map = results[("0", "0")]
     for key, (egos, gmap) in results.items():
         assert torch.equal(gmap, ref_map), key

@@ -278,3 +278,4 @@ def test_random_small_geometries_match_spec():
             assert np.array_equal(g_emul, g_spec)
 
     run()
+

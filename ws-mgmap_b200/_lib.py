@@ -19,7 +19,7 @@ class WsmgDims(ctypes.Structure):
 
 class WsmgOpts(ctypes.Structure):
     _fields_ = [("trig", ctypes.c_void_p), ("ego_half", ctypes.c_void_p), ("env_slots", ctypes.c_void_p),
-                ("ev_before_fused", ctypes.c_void_p), ("ev_after_fused", ctypes.c_void_p)]
+                ("ev_before_fused", ctypes.c_void_p), ("ev_after_fused", ctypes.c_void_p), ("status", ctypes.c_void_p)]
 
 
 _P = ctypes.c_void_p
@@ -29,14 +29,14 @@ _OP = ctypes.POINTER(WsmgOpts)
 SIGNATURES = {
     "wsmg_abi_version": (ctypes.c_int, []),
     "wsmg_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "wsmg_debug_switches": (None, [ctypes.c_int, ctypes.c_int]),
     "wsmg_scratch_bytes": (ctypes.c_size_t, [_DP]),
     "wsmg_scratch_flags_offset": (ctypes.c_size_t, [_DP]),
     "wsmg_map_update": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
     "wsmg_map_update_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _OP, _P, ctypes.c_size_t, _DP, _P]),
-    "wsmg_map_update_timed": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P, _P, _P]),
     "wsmg_unproject_index": (ctypes.c_int, [_P, _P, _P, _DP, _P]),
     "wsmg_scatter_max": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
-    "wsmg_register_fuse_retrieve": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _DP, _P]),
+    "wsmg_register_fuse_retrieve": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _DP, _P]),
     "wsmg_base_coords_host": (ctypes.c_int, [_P, ctypes.c_int32]),
     "wsmg_host_staging_bytes": (ctypes.c_size_t, [_DP, ctypes.c_int32]),
     "wsmg_map_update_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int32, _DP, _P]),
@@ -47,8 +47,10 @@ SIGNATURES = {
                                                ctypes.c_uint32, _P]),
 }
 
+ABI_VERSION = 3
 FLAG_INVALID_PIXEL = 1
 FLAG_OUTSIDE_FAN = 2
+FLAG_BAD_SLOT = 4
 
 _lib = None
 
@@ -62,21 +64,27 @@ class WsmgError(RuntimeError):
 
 
 def load() -> ctypes.CDLL:
-    """Load libwsmg.so (building it in-tree if the sources are newer / it is missing and nvcc exists)."""
+    """Load libwsmg.so.  Where nvcc exists (the build container) the library is first rebuilt in-tree if it is
+    missing or older than its sources (build.build_cuda compares mtimes, a no-op otherwise); on a box without
+    nvcc the shipped .so is used as it is, and a missing one raises -- there is no fallback."""
     global _lib
     if _lib is not None:
         return _lib
     path = os.environ.get("WSMG_LIB_PATH", LIB_PATH)    # override: profiling builds (build.py --phase-skip)
+    if path == LIB_PATH:
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from .build import build_cuda
+            build_cuda()
     if not os.path.exists(path):
-        from .build import build_cuda
-        build_cuda()
+        raise WsmgError(f"{path} is missing and cannot be built here (no nvcc): run python ws-mgmap_b200/build.py")
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.wsmg_abi_version() != 2:
-        raise WsmgError(f"libwsmg ABI {lib.wsmg_abi_version()} != 2")
+    if lib.wsmg_abi_version() != ABI_VERSION:
+        raise WsmgError(f"libwsmg ABI {lib.wsmg_abi_version()} != {ABI_VERSION} (stale build? python ws-mgmap_b200/build.py -f)")
     _lib = lib
     return lib
 

@@ -23,11 +23,28 @@ NVCC_FLAGS = [
 ]
 
 
-def _newer(target: str, sources) -> bool:
-    if not os.path.exists(target):
+def _digest(sources, extra="") -> str:
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for s in sources:
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _newer(target: str, sources, extra="") -> bool:
+    """True when `target` was built from exactly these sources (content hash in target + '.stamp'; file times do
+    not survive the copy to the GPU box)."""
+    stamp = target + ".stamp"
+    if not (os.path.exists(target) and os.path.exists(stamp)):
         return False
-    t = os.path.getmtime(target)
-    return all(os.path.getmtime(s) <= t for s in sources)
+    with open(stamp) as f:
+        return f.read().strip() == _digest(sources, extra)
+
+
+def _stamp(target: str, sources, extra=""):
+    with open(target + ".stamp", "w") as f:
+        f.write(_digest(sources, extra))
 
 
 def _sources():
@@ -55,6 +72,7 @@ def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = Fa
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    _stamp(target, _sources())
     return target
 
 
@@ -69,6 +87,7 @@ def build_emulation(force: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    _stamp(target, _sources())
     return target
 
 

@@ -1,7 +1,8 @@
 // libwsmg.so -- WS-MGMap per-step map update for B200 (sm_100a).  C ABI in include/wsmg.h.
 //
 // Three launches per step, all on the caller's stream:
-//   k_reset   episode-reset mask over the whole NHWC map       (rgb_mapping.py:35); per-env rotation column bounds
+//   k_reset   episode-reset mask over the whole NHWC map       (rgb_mapping.py:35); per-env rotation sines / cosines
+//             and column bounds
 //   k_cells   fused unproject + height-band test + bin + index  (rgb_mapping.py:153-176, 188-217)
 //   k_fused   one CTA per (env, 4-channel slab): shared-memory scatter-max, rotate, translate,
 //             max-fuse into the map window, translate back, crop, rotate -> NCHW ego map
@@ -20,19 +21,28 @@
 
 namespace wsmg {
 
-constexpr int FUSED_THREADS = FUSED_NT;
 constexpr int CELLS_THREADS = 256;
 
 // ------------------------------------------------------------------ k_reset
-// full_global_map[:bs] *= masks (rgb_mapping.py:35).  mask == 1 (the steady state) touches nothing.
+// Per-env preparation, grid (bs, chunks):
+//   * full_global_map[:bs] *= masks (rgb_mapping.py:35); mask == 1 (the steady state) touches nothing;
+//   * clears the env flags (k_cells, the next launch, sets them);
+//   * once per env: both rotations' cos / sin exactly as the rotations will use them, and the per-row column bounds
+//     outside which the first rotation cannot see the fan (rot_row_bounds, wsmg_body.h);
+//   * flags an env slot that is not a row of the map tensor (the frame is then skipped everywhere).
 __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
                                                size_t per_env, uint32_t* __restrict__ env_flags,
                                                const int32_t* __restrict__ env_slots, int32_t* __restrict__ row_bounds,
                                                float* __restrict__ env_trig, const float* __restrict__ compass,
-                                               const float* __restrict__ trig, Geo g) {
-  const int b = blockIdx.y;
-  if (env_flags != nullptr && blockIdx.x == 0 && threadIdx.x == 0) env_flags[b] = 0u;   // k_cells (next launch) sets them
-  if (row_bounds != nullptr && blockIdx.x == gridDim.x - 1) {     // per-env column bounds of the first rotation (wsmg_body.h)
+                                               const float* __restrict__ trig, uint32_t* __restrict__ status, int n_maps, Geo g) {
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int mrow = env_slots != nullptr ? env_slots[b] : b;
+  const bool bad_slot = gmap != nullptr && (unsigned)mrow >= (unsigned)n_maps;
+  if (chunk == 0 && threadIdx.x == 0) {
+    if (env_flags != nullptr) env_flags[b] = bad_slot ? WSMG_FLAG_BAD_SLOT : 0u;
+    if (bad_slot && status != nullptr) status[1] = 1u;
+  }
+  if (row_bounds != nullptr && chunk == gridDim.y - 1) {
     float cs, sn;
     if (trig != nullptr) { cs = trig[4 * b + 0]; sn = trig[4 * b + 1]; }
     else { const float h = -compass[b]; sn = sinf(h); cs = cosf(h); }
@@ -44,12 +54,12 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
       env_trig[4 * b + 0] = cs; env_trig[4 * b + 1] = sn; env_trig[4 * b + 2] = cs2; env_trig[4 * b + 3] = sn2;
     }
   }
-  if (gmap == nullptr) return;
+  if (gmap == nullptr || bad_slot) return;
   const float m = mask[b];
   if (m == 1.0f) return;
-  float* base = gmap + (size_t)(env_slots != nullptr ? env_slots[b] : b) * per_env;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float* base = gmap + (size_t)mrow * per_env;
+  const size_t stride = (size_t)gridDim.y * blockDim.x;
+  size_t i = (size_t)chunk * blockDim.x + threadIdx.x;
   if ((per_env & 3) == 0) {
     float4* b4 = reinterpret_cast<float4*>(base);
     const size_t n4 = per_env >> 2;
@@ -83,17 +93,18 @@ constexpr int CELLS_MAX_W = 1024;
 template <bool STAGE_API>
 __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
                                                           int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
-                                                          uint32_t* __restrict__ env_flags, Geo g, int stage_rows) {
+                                                          uint32_t* __restrict__ env_flags, uint32_t* __restrict__ status, Geo g, int stage_rows) {
   extern __shared__ __align__(128) unsigned char cells_smem[];
   __shared__ int rowoff[160];
   __shared__ __align__(16) int col_src[CELLS_MAX_W];
   __shared__ __align__(16) float col_xx[CELLS_MAX_W];
   __shared__ __align__(8) uint64_t bar;
   float* drows = reinterpret_cast<float*>(cells_smem);       // [stage_rows][Wd] when stage_rows > 0
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;
+
   const int HW = g.Hf * g.Wf;
   const int per_block = CELLS_THREADS * CELLS_PX * CELLS_GROUPS;
-  const int t_first = blockIdx.x * per_block;
+  const int t_first = blockIdx.y * per_block;
   const int t_last = (t_first + per_block < HW ? t_first + per_block : HW) - 1;
   const float* depth_b = depth + (size_t)b * g.Hd * g.Wd;
   const int r_first = sample_index(g, t_first / g.Wf);
@@ -171,15 +182,17 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   const unsigned outl = __ballot_sync(0xFFFFFFFFu, any_outlier);
   if (env_flags != nullptr && (bad | outl) != 0u && (threadIdx.x & 31) == 0)
     atomicOr(env_flags + b, (bad ? WSMG_FLAG_INVALID_PIXEL : 0u) | (outl ? WSMG_FLAG_OUTSIDE_FAN : 0u));
+  if (status != nullptr && outl != 0u && (threadIdx.x & 31) == 0) status[0] = 1u;   // sticky, polled by the host at its next call
 }
 
 // ------------------------------------------------------------------ k_fused
 template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL>
-__global__ void __launch_bounds__(FUSED_THREADS, 1) k_fused(const __grid_constant__ FusedParams p) {
-  // One CTA per (env, slab).  (A persistent one-CTA-per-SM loop over the items was measured and is not faster:
-  // the hardware already overlaps CTA launch with the previous CTA's tail, and static striding loses balance.)
+__global__ void __launch_bounds__(FUSED_NT, 1) k_fused(const __grid_constant__ FusedParams p) {
+  // One CTA per (env, slab).  (A persistent loop over the items was measured twice -- one 1024-thread CTA per SM in
+  // round 1, two 512-thread CTAs per SM in round 2 -- and is not faster: the hardware already overlaps CTA launch with
+  // the previous CTA's tail.)
   extern __shared__ __align__(1024) unsigned char smem[];
-  fused_body<FUSED_THREADS, CE, CG, CHW, VEC, TMA, POOL>(p, blockIdx.x, smem, threadIdx.x);
+  fused_body<FUSED_NT, CE, CG, CHW, VEC, TMA, POOL>(p, blockIdx.x, smem, threadIdx.x);
 }
 
 // ------------------------------------------------------------------ k_semcrop
@@ -205,34 +218,58 @@ __global__ void __launch_bounds__(256) k_semcrop(const float* __restrict__ maps,
 // ------------------------------------------------------------------ host glue
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int launch_reset(float* gmap, const float* mask, uint32_t* env_flags, const int32_t* env_slots, const wsmg_dims* d,
-                        cudaStream_t s, int32_t* row_bounds = nullptr, float* env_trig = nullptr,
-                        const float* compass = nullptr, const float* trig = nullptr) {
+// Geometry constants and the shared-memory plan of the last dims seen by this host thread (a trainer calls with the
+// same shapes step after step; make_geo evaluates a tangent and sums the fan, make_plan sizes the ring).
+struct GeoPlan { Geo g; SmemPlan sp; };
+static const GeoPlan& geo_plan(const wsmg_dims* d) {
+  static thread_local wsmg_dims last{};
+  static thread_local GeoPlan gp;
+  static thread_local bool valid = false;
+  const bool same = valid && d->C == last.C && d->Hf == last.Hf && d->Wf == last.Wf && d->Hd == last.Hd && d->Wd == last.Wd &&
+                    d->E == last.E && d->G == last.G && d->resolution == last.resolution && d->C_in == last.C_in;   // (bs, n_maps: not geometry)
+  if (!same) {
+    gp.g = make_geo(d);
+    gp.sp = make_plan(gp.g);
+    last = *d;
+    valid = true;
+  }
+  return gp;
+}
+
+struct ResetArgs {      // optional outputs of k_reset beyond the mask reset
+  uint32_t* env_flags = nullptr; const int32_t* env_slots = nullptr; int32_t* row_bounds = nullptr;
+  float* env_trig = nullptr; const float* compass = nullptr; const float* trig = nullptr; uint32_t* status = nullptr;
+};
+
+static int launch_reset(float* gmap, const float* mask, const wsmg_dims* d, cudaStream_t s, const ResetArgs& a) {
   const size_t per_env = (size_t)d->G * d->G * d->C;
-  dim3 grid(gmap ? 16 : 1, d->bs);
-  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, env_flags, env_slots, row_bounds, env_trig, compass, trig, make_geo(d));
+  dim3 grid(d->bs, gmap ? 16 : 1);
+  k_reset<<<grid, 256, 0, s>>>(gmap, mask, per_env, a.env_flags, a.env_slots, a.row_bounds, a.env_trig, a.compass, a.trig,
+                              a.status, d->n_maps, geo_plan(d).g);
   return (int)cudaGetLastError();
 }
 
 static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, uint32_t* env_flags,
-                        const Geo& g, int bs, cudaStream_t s) {
+                        uint32_t* status, const Geo& g, int bs, cudaStream_t s) {
   if (g.fan_rows > 160 || g.Wf > CELLS_MAX_W) return WSMG_E_DIMS;
   const int HW = g.Hf * g.Wf;
   const int per_block = CELLS_THREADS * CELLS_PX * CELLS_GROUPS;
-  dim3 grid((HW + per_block - 1) / per_block, bs);
+  dim3 grid(bs, (HW + per_block - 1) / per_block);
+  if (grid.y > 65535u) return WSMG_E_DIMS;
   // depth rows one block can touch: its sampled rows (per_block / Wf + 2) times the subsampling ratio, + 1
   int stage_rows = (int)((per_block / g.Wf + 2) * (double)g.Hd / g.Hf) + 2;
   size_t smem = (size_t)stage_rows * g.Wd * 4;
   const bool bulk_ok = (g.Wd % 4) == 0 && (((size_t)g.Hd * g.Wd) % 4) == 0 && (reinterpret_cast<uintptr_t>(depth) & 15u) == 0;
   if (smem > 32 * 1024 || !bulk_ok) { stage_rows = 0; smem = 0; }     // fall back to direct global gathers
-  if (lin != nullptr || invalid != nullptr) k_cells<true><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, g, stage_rows);
-  else k_cells<false><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, g, stage_rows);
+  if (lin != nullptr || invalid != nullptr) k_cells<true><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, status, g, stage_rows);
+  else k_cells<false><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, status, g, stage_rows);
   return (int)cudaGetLastError();
 }
 
 // CUtensorMap of the caller's NHWC map [n_maps, G, G, C] with a box of {4 ch, WWP cols, TMA_ROWS rows, 1}.
-// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
-static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const Geo& g) {
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).  The last encoding is
+// kept per host thread: a trainer calls with the same map tensor step after step.
+static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const Geo& g, int wwp) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -246,64 +283,110 @@ static int encode_window_map(TensorMapBlob* out, float* gmap, int n_maps, const 
     fn = (encode_fn)ptr;
   }
   static_assert(sizeof(CUtensorMap) <= sizeof(TensorMapBlob), "tensor map blob too small");
+  struct Key { float* gmap; int n_maps, G, C, wwp; };
+  static thread_local Key last_key = {nullptr, 0, 0, 0, 0};
+  static thread_local TensorMapBlob last_blob;
+  if (last_key.gmap == gmap && last_key.n_maps == n_maps && last_key.G == g.G && last_key.C == g.C && last_key.wwp == wwp) {
+    *out = last_blob;
+    return 0;
+  }
   CUtensorMap tm;
   const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.G, (cuuint64_t)g.G, (cuuint64_t)n_maps};
   const cuuint64_t strides[3] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.G * g.C * 4, (cuuint64_t)g.G * g.G * g.C * 4};
-  const cuuint32_t box[4] = {4, (cuuint32_t)make_plan(g).wwp, (cuuint32_t)TMA_ROWS, 1};   // see prefetch_band
+  const cuuint32_t box[4] = {4, (cuuint32_t)wwp, (cuuint32_t)TMA_ROWS, 1};   // see prefetch_band
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gmap, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   memcpy(out->bytes, &tm, sizeof(tm));
+  last_key = Key{gmap, n_maps, g.G, g.C, wwp};
+  last_blob = *out;
   return 0;
 }
 
-template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL = false>
-static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+// Per-device constants and per-process switches, looked up once.
+struct DeviceInfo { int sms = 0, max_optin = 0, dev = 0; };
+static int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  k_fused<CE, CG, CHW, VEC, TMA, POOL><<<grid, FUSED_THREADS, p.sp.total, s>>>(p);
+  if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+  if (cache[dev].sms == 0) {
+    DeviceInfo di;
+    if ((e = cudaDeviceGetAttribute(&di.max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    di.dev = dev;
+    cache[dev] = di;
+  }
+  *out = cache[dev];
+  return 0;
+}
+// WSMG_FORCE_GENERIC=1 routes the reference shapes through the runtime-geometry kernel, WSMG_NO_TMA=1
+// moves the map window with cp.async / st.global instead of TMA (both for tests and A/B profiling); read once.
+// wsmg_debug_switches() overrides them at run time (tests compare the four builds inside one process).
+struct Switches { bool generic, no_tma; };
+static int g_switch_override = -1;          // -1: environment; else bit 0 = generic, bit 1 = no TMA
+static Switches switches() {
+  static const Switches env = [] {
+    Switches s{};
+    const char* f = getenv("WSMG_FORCE_GENERIC");
+    const char* n = getenv("WSMG_NO_TMA");
+    s.generic = f && f[0] == '1';
+    s.no_tma = n && n[0] == '1';
+    return s;
+  }();
+  const int o = g_switch_override;
+  if (o < 0) return env;
+  Switches s{(o & 1) != 0, (o & 2) != 0};
+  return s;
+}
+
+template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL = false>
+static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s, int dev) {
+  static int attr_set_for[64] = {0};          // dynamic shared memory opt-in, once per device and size
+  if (attr_set_for[dev] < p.sp.total) {
+    cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+    if (e != cudaSuccess) return (int)e;
+    attr_set_for[dev] = p.sp.total;
+  }
+  k_fused<CE, CG, CHW, VEC, TMA, POOL><<<grid, FUSED_NT, p.sp.total, s>>>(p);
   return (int)cudaGetLastError();
 }
 
-// WSMG_FORCE_GENERIC=1 routes the reference shapes through the runtime-geometry kernel, WSMG_NO_TMA=1
-// moves the map window with cp.async / st.global instead of TMA (both for tests and A/B profiling).
-static int launch_fused(FusedParams p, int n_maps, cudaStream_t s) {
-  p.sp = make_plan(p.g);
-  int dev = 0, max_optin = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (e != cudaSuccess) return (int)e;
-  if (p.sp.total > max_optin) return WSMG_E_SMEM;
+static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s) {
+  p.sp = geo_plan(d).sp;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != 0) return rc;
+  if (p.sp.total > di.max_optin) return WSMG_E_SMEM;
   const bool vec = (p.g.C % 4) == 0;
+  p.n_maps = d->n_maps;
   const int grid = p.bs * ((p.g.C + SLAB - 1) / SLAB);
-  const char* force = getenv("WSMG_FORCE_GENERIC");
-  const char* no_tma = getenv("WSMG_NO_TMA");
   p.debug_skip = 0;
 #if defined(WSMG_PHASE_SKIP)
   if (const char* dbg = getenv("WSMG_DEBUG_SKIP")) p.debug_skip = atoi(dbg);   // profiling build only, see WSMG_SKIP
 #endif
-  const bool generic = force && force[0] == '1';
-  bool tma = vec && !p.stop_after_scatter && !(no_tma && no_tma[0] == '1') && p.sp.wwp <= p.g.G;   // box no wider than the map
+  const Switches sw = switches();
+  bool tma = vec && !p.stop_after_scatter && !sw.no_tma && p.sp.wwp <= p.g.G;   // box no wider than the map
   if (tma) {
-    int rc = encode_window_map(&p.tmap, p.gmap, n_maps, p.g);
+    rc = encode_window_map(&p.tmap, p.gmap, d->n_maps, p.g, p.sp.wwp);
     if (rc != 0) return rc;
   }
   if (p.g.Cin != p.g.C) {                                   // channel pool fused in the scatter: run-time geometry builds
-    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s);
-    return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s);
+    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s, di.dev) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s, di.dev);
+    return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s, di.dev);
   }
-  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !generic;
+  const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !sw.generic;
   if (ref_geo && p.g.Hf * p.g.Wf == 224 * 224) {          // the reference's shapes (vlnce_task.yaml:11-18)
-    return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s)
-               : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s);
+    return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s, di.dev)
+               : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s, di.dev);
   }
   if (ref_geo && p.g.Hf * p.g.Wf == 256 * 256 && tma) {   // BASELINE.json's wording: features at the depth resolution
-    return launch_fused_t<100, 240, 256 * 256, true, true>(p, grid, s);
+    return launch_fused_t<100, 240, 256 * 256, true, true>(p, grid, s, di.dev);
   }
-  if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s) : launch_fused_t<0, 0, 0, true, false>(p, grid, s);
-  return launch_fused_t<0, 0, 0, false, false>(p, grid, s);
+  if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s, di.dev) : launch_fused_t<0, 0, 0, true, false>(p, grid, s, di.dev);
+  return launch_fused_t<0, 0, 0, false, false>(p, grid, s, di.dev);
 }
 
 }  // namespace wsmg
@@ -313,6 +396,10 @@ using namespace wsmg;
 extern "C" {
 
 int wsmg_abi_version(void) { return WSMG_ABI_VERSION; }
+
+void wsmg_debug_switches(int force_generic, int no_tma) {
+  g_switch_override = (force_generic < 0 || no_tma < 0) ? -1 : ((force_generic ? 1 : 0) | (no_tma ? 2 : 0));
+}
 
 const char* wsmg_error_string(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -338,41 +425,40 @@ int wsmg_base_coords_host(float* out_host, int32_t n) {
 }
 
 static int map_update_impl(const float* feat, const float* depth, const float* gps, const float* compass,
-                           const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
-                           size_t scratch_bytes_, const wsmg_dims* d, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1,
-                           void* ego_half = nullptr, const int32_t* env_slots = nullptr) {
+                           const float* mask, float* gmap, float* ego_out, const wsmg_opts* o, void* scratch,
+                           size_t scratch_bytes_, const wsmg_dims* d, cudaStream_t s) {
   int rc = validate_dims(d);
   if (rc != WSMG_OK) return rc;
   if (!feat || !depth || !gps || !compass || !mask || !gmap || !ego_out || !scratch) return WSMG_E_NULL;
   if (!aligned16(feat) || !aligned16(gmap) || !aligned16(scratch)) return WSMG_E_ALIGN;
   if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
-  const Geo g = make_geo(d);
-  uint16_t* codes = (uint16_t*)scratch;
-  uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
-  int32_t* bounds = (int32_t*)((unsigned char*)flags + scratch_flags_bytes(d));
-  float* env_trig = (float*)((unsigned char*)bounds + scratch_bounds_bytes(d));
-  rc = launch_reset(gmap, mask, flags, env_slots, d, s, bounds, env_trig, compass, trig);
+  const Geo& g = geo_plan(d).g;
+  const ScratchView sv = scratch_view(scratch, d);
+  ResetArgs ra;
+  ra.env_flags = sv.flags; ra.env_slots = o->env_slots; ra.row_bounds = sv.bounds;
+  ra.env_trig = sv.env_trig; ra.compass = compass; ra.trig = o->trig; ra.status = o->status;
+  rc = launch_reset(gmap, mask, d, s, ra);
   if (rc) return rc;
-  rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
+  rc = launch_cells(depth, sv.codes, nullptr, nullptr, sv.flags, o->status, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
-  p.row_bounds = bounds;
-  p.env_trig = env_trig;
-  p.feat = feat; p.codes = codes; p.env_flags = flags; p.gps = gps; p.compass = compass; p.trig = trig;
+  p.row_bounds = sv.bounds; p.env_trig = sv.env_trig; p.status = o->status;
+  p.feat = feat; p.codes = sv.codes; p.env_flags = sv.flags; p.gps = gps; p.compass = compass; p.trig = o->trig;
   p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
-  p.ego_half = (uint16_t*)ego_half; p.env_slots = env_slots;
+  p.ego_half = (uint16_t*)o->ego_half; p.env_slots = o->env_slots;
   p.stop_after_scatter = 0; p.bs = d->bs; p.g = g;
-  if (ev0) cudaEventRecord(ev0, s);
-  rc = launch_fused(p, d->n_maps, s);
-  if (ev1) cudaEventRecord(ev1, s);
+  if (o->ev_before_fused) cudaEventRecord((cudaEvent_t)o->ev_before_fused, s);
+  rc = launch_fused(p, d, s);
+  if (o->ev_after_fused) cudaEventRecord((cudaEvent_t)o->ev_after_fused, s);
   return rc;
 }
 
 int wsmg_map_update(const float* feat, const float* depth, const float* gps, const float* compass,
                     const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
                     size_t scratch_bytes_, const wsmg_dims* d, void* stream) {
-  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, trig, scratch, scratch_bytes_, d,
-                         (cudaStream_t)stream, nullptr, nullptr);
+  wsmg_opts o{};
+  o.trig = trig;
+  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, &o, scratch, scratch_bytes_, d, (cudaStream_t)stream);
 }
 
 int wsmg_map_update_ex(const float* feat, const float* depth, const float* gps, const float* compass,
@@ -380,24 +466,14 @@ int wsmg_map_update_ex(const float* feat, const float* depth, const float* gps, 
                        size_t scratch_bytes_, const wsmg_dims* d, void* stream) {
   wsmg_opts z{};
   if (o == nullptr) o = &z;
-  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, o->trig, scratch, scratch_bytes_, d,
-                         (cudaStream_t)stream, (cudaEvent_t)o->ev_before_fused, (cudaEvent_t)o->ev_after_fused,
-                         o->ego_half, o->env_slots);
-}
-
-int wsmg_map_update_timed(const float* feat, const float* depth, const float* gps, const float* compass,
-                          const float* mask, float* gmap, float* ego_out, const float* trig, void* scratch,
-                          size_t scratch_bytes_, const wsmg_dims* d, void* stream, void* ev_before_fused,
-                          void* ev_after_fused) {
-  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, trig, scratch, scratch_bytes_, d,
-                         (cudaStream_t)stream, (cudaEvent_t)ev_before_fused, (cudaEvent_t)ev_after_fused);
+  return map_update_impl(feat, depth, gps, compass, mask, gmap, ego_out, o, scratch, scratch_bytes_, d, (cudaStream_t)stream);
 }
 
 int wsmg_unproject_index(const float* depth, int32_t* lin, uint8_t* invalid, const wsmg_dims* d, void* stream) {
   int rc = validate_dims(d);
   if (rc != WSMG_OK) return rc;
   if (!depth || !lin || !invalid) return WSMG_E_NULL;
-  return launch_cells(depth, nullptr, lin, invalid, nullptr, make_geo(d), d->bs, (cudaStream_t)stream);
+  return launch_cells(depth, nullptr, lin, invalid, nullptr, nullptr, make_geo(d), d->bs, (cudaStream_t)stream);
 }
 
 int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out, void* scratch, size_t scratch_bytes_,
@@ -409,33 +485,62 @@ int wsmg_scatter_max(const float* feat, const float* depth, float* proj_out, voi
   if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
   cudaStream_t s = (cudaStream_t)stream;
   const Geo g = make_geo(d);
-  uint16_t* codes = (uint16_t*)scratch;
-  uint32_t* flags = (uint32_t*)((unsigned char*)scratch + scratch_codes_bytes(d));
-  rc = launch_reset(nullptr, nullptr, flags, nullptr, d, s);      // only clears the env flags
+  const ScratchView sv = scratch_view(scratch, d);
+  ResetArgs ra;
+  ra.env_flags = sv.flags;
+  rc = launch_reset(nullptr, nullptr, d, s, ra);      // only clears the env flags
   if (rc) return rc;
-  rc = launch_cells(depth, codes, nullptr, nullptr, flags, g, d->bs, s);
+  rc = launch_cells(depth, sv.codes, nullptr, nullptr, sv.flags, nullptr, g, d->bs, s);
   if (rc) return rc;
   FusedParams p{};
-  p.feat = feat; p.codes = codes; p.env_flags = flags; p.proj_out = proj_out; p.stop_after_scatter = 1; p.bs = d->bs; p.g = g;
-  return launch_fused(p, d->n_maps, s);
+  p.feat = feat; p.codes = sv.codes; p.env_flags = sv.flags; p.proj_out = proj_out; p.stop_after_scatter = 1; p.bs = d->bs; p.g = g;
+  return launch_fused(p, d, s);
 }
 
 int wsmg_register_fuse_retrieve(const float* proj_in, const float* gps, const float* compass, const float* mask,
-                                float* gmap, float* ego_out, const float* trig, const wsmg_dims* d, void* stream) {
+                                float* gmap, float* ego_out, const float* trig, void* scratch, size_t scratch_bytes_,
+                                const wsmg_dims* d, void* stream) {
   int rc = validate_dims(d);
   if (rc != WSMG_OK) return rc;
-  if (!proj_in || !gps || !compass || !mask || !gmap || !ego_out) return WSMG_E_NULL;
-  if (!aligned16(gmap)) return WSMG_E_ALIGN;
+  if (!proj_in || !gps || !compass || !mask || !gmap || !ego_out || !scratch) return WSMG_E_NULL;
+  if (!aligned16(gmap) || !aligned16(scratch)) return WSMG_E_ALIGN;
+  if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
   cudaStream_t s = (cudaStream_t)stream;
-  rc = launch_reset(gmap, mask, nullptr, nullptr, d, s);
+  const ScratchView sv = scratch_view(scratch, d);
+  ResetArgs ra;
+  ra.row_bounds = sv.bounds; ra.env_trig = sv.env_trig; ra.compass = compass; ra.trig = trig;
+  rc = launch_reset(gmap, mask, d, s, ra);
   if (rc) return rc;
   FusedParams p{};
+  p.row_bounds = sv.bounds; p.env_trig = sv.env_trig;
   p.proj_in = proj_in; p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap; p.ego = ego_out;
   p.bs = d->bs; p.g = make_geo(d);
-  return launch_fused(p, d->n_maps, s);
+  return launch_fused(p, d, s);
 }
 
 // ------------------------------------------------------------------ host-buffer entry
+// Internal copy / compute lanes of the host-buffer entry: two non-blocking streams, a fork and two join events, per
+// host thread and device, created on first use and kept for the life of the thread.
+struct HostLanes { cudaStream_t st[2]; cudaEvent_t fork, join[2]; bool ready; };
+static int host_lanes(HostLanes** out) {
+  static thread_local HostLanes lanes[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+  HostLanes& l = lanes[dev];
+  if (!l.ready) {
+    if ((e = cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+    for (int i = 0; i < 2; ++i) {
+      if ((e = cudaStreamCreateWithFlags(&l.st[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+      if ((e = cudaEventCreateWithFlags(&l.join[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+    }
+    l.ready = true;
+  }
+  *out = &l;
+  return 0;
+}
+
 // staging layout per chunk slot (2 slots): feat | depth | gps | compass | mask | ego | scratch
 struct HostSlot { float *feat, *depth, *gps, *compass, *mask, *ego; void* scratch; size_t scratch_bytes; };
 
@@ -553,19 +658,18 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
     for (int j = 0; j < d->Wf; ++j) { col_src[j] = sample_index(g, j); col_xx[j] = pinhole_xx(g, col_src[j]); }
   }
   cudaStream_t user = (cudaStream_t)stream;
-  // two internal streams ping-pong over the two staging slots so that the copies of chunk i+1
-  // overlap the kernels of chunk i; both are fenced against the caller's stream with events.
-  cudaStream_t st[2];
-  cudaEvent_t fork, join[2];
+  // Two internal streams ping-pong over the two staging slots so that the copies of chunk i+1 overlap the kernels of
+  // chunk i; both are fenced against the caller's stream with events.  Streams and events are created once per host
+  // thread and device and kept (a trainer calls this every step).
+  HostLanes* lanes = nullptr;
+  rc = host_lanes(&lanes);
+  if (rc != 0) return rc;
+  cudaStream_t* st = lanes->st;
   cudaError_t e;
-  if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-  for (int i = 0; i < 2; ++i) {
-    if ((e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-    if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-  }
-  cudaEventRecord(fork, user);
-  cudaStreamWaitEvent(st[0], fork, 0);
-  cudaStreamWaitEvent(st[1], fork, 0);
+  auto ck = [&](cudaError_t err) { if (err != cudaSuccess && rc == 0) rc = (int)err; };
+  ck(cudaEventRecord(lanes->fork, user));
+  ck(cudaStreamWaitEvent(st[0], lanes->fork, 0));
+  ck(cudaStreamWaitEvent(st[1], lanes->fork, 0));
   const size_t one = slot_bytes(d, chunk, nullptr, nullptr);
   const size_t per_map = (size_t)d->G * d->G * d->C;
   int slot = 0;
@@ -586,28 +690,28 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
         live_rows_host(g, depth_host + (size_t)(b0 + k) * de, col_src, col_xx, &lo, &hi);
         if (lo > hi) continue;                                   // nothing in this frame can write
         const size_t first = (size_t)lo * d->Wf;
-        cudaMemcpy2DAsync(hs.feat + (size_t)k * fe + first, pitch, feat_host + (size_t)(b0 + k) * fe + first, pitch,
-                          (size_t)(hi - lo + 1) * d->Wf * 4, planes, cudaMemcpyHostToDevice, s);
+        ck(cudaMemcpy2DAsync(hs.feat + (size_t)k * fe + first, pitch, feat_host + (size_t)(b0 + k) * fe + first, pitch,
+                             (size_t)(hi - lo + 1) * d->Wf * 4, planes, cudaMemcpyHostToDevice, s));
       }
     } else {
-      cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s);
+      ck(cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s));
     }
-    cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(hs.compass, compass_host + b0, n * 4, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(hs.mask, mask_host + b0, n * 4, cudaMemcpyHostToDevice, s);
+    ck(cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s));
+    ck(cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s));
+    ck(cudaMemcpyAsync(hs.compass, compass_host + b0, n * 4, cudaMemcpyHostToDevice, s));
+    ck(cudaMemcpyAsync(hs.mask, mask_host + b0, n * 4, cudaMemcpyHostToDevice, s));
+    if (rc != 0) break;
     wsmg_dims dc = *d; dc.bs = n; dc.n_maps = n;
     rc = wsmg_map_update(feat_mapped != nullptr ? feat_mapped + b0 * fe : hs.feat, hs.depth, hs.gps, hs.compass, hs.mask, gmap + b0 * per_map, hs.ego, nullptr,
                          hs.scratch, hs.scratch_bytes, &dc, s);
-    if (rc == 0) cudaMemcpyAsync(ego_out_host + b0 * ee, hs.ego, n * ee * 4, cudaMemcpyDeviceToHost, s);
+    if (rc == 0) ck(cudaMemcpyAsync(ego_out_host + b0 * ee, hs.ego, n * ee * 4, cudaMemcpyDeviceToHost, s));
   }
+  // always rejoin the caller's stream, also after an error: nothing may outlive the call unordered
   for (int i = 0; i < 2; ++i) {
-    cudaEventRecord(join[i], st[i]);
-    cudaStreamWaitEvent(user, join[i], 0);
+    e = cudaEventRecord(lanes->join[i], st[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(user, lanes->join[i], 0);
+    ck(e);
   }
-  // streams/events are released once their work drains (CUDA defers destruction)
-  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(st[i]); cudaEventDestroy(join[i]); }
-  cudaEventDestroy(fork);
   if (rc == 0) rc = (int)cudaGetLastError();
   return rc;
 }

@@ -17,6 +17,14 @@
 //     for which a non-negative float is its own key (profiles/: match_any+redux aggregation is 39x slower);
 //     its loop is statically strided and unrolled so that queues and slots are register names.
 //
+// Round 2 measured two restructurings of this body and kept neither (branches two-cta-experiment and
+// plan-tables-experiment, summaries in profiles/r02_*):
+//   * two 512-thread CTAs per SM (compact rotated grid, crop rows in an L2-resident global slot, tiled output
+//     rotation): +24 % instructions for +4 points of issue utilisation, k_fused 3.91 -> 4.45 ms;
+//   * per-env plan tables (taps / weights precomputed once per env instead of by each of its 16 slab CTAs):
+//     -20 % instructions, but the crop and the output rotation are bound by the LSU pipe (tap wavefronts + store tag
+//     work), not by issue, and one more 16-byte load per cell made them slower: 4.03-4.58 ms.
+//
 // Shared memory (E=100, G=240: 229 KB of the 227 KiB a CTA may opt in to):
 //   X     [1 + E*E] F4    zero cell + (during the scatter) the per-thread cp.async feature slots, then the
 //                         rotated ego grid R; its rows are overwritten by the crop B behind the fuse front
@@ -127,6 +135,8 @@ struct FusedParams {
   const int32_t* env_slots; // optional [bs]: map row of frame b (default b)
   const int32_t* row_bounds; // optional [bs,E]: rot_row_bounds per env and R row (k_reset); null = no bounds
   const float* env_trig;    // optional [bs,4]: {cos, sin}(-compass), {cos, sin}(+compass) per env (k_reset); null = evaluate here
+  uint32_t* status;         // optional uint32[2], device-accessible (pinned host memory): see wsmg_opts.status
+  int n_maps;               // rows of the caller's map tensor (an env slot outside [0, n_maps) skips its frame)
   float* proj_out;          // optional dump of the pre-rotation grid [bs,C,E,E]
   const float* proj_in;     // optional: take the grid from here instead of scattering
   int stop_after_scatter;   // stage API: return after writing proj_out
@@ -364,6 +374,10 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float* gmap_b = nullptr;
   const int mrow = p.env_slots != nullptr ? p.env_slots[b] : b;      // row of the caller's map tensor
   if (!p.stop_after_scatter) {
+    if ((unsigned)mrow >= (unsigned)p.n_maps) {               // not a row of the map: skip the frame (k_reset flags it)
+      if (tid == 0 && p.status != nullptr) p.status[1] = 1u;
+      return;
+    }
     float gxc, gyc;
     gps_cell(g, p.gps[2 * b], p.gps[2 * b + 1], &gxc, &gyc);
     float sy = gxc - gcenter, sx = gyc - gcenter;

@@ -85,6 +85,7 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
   p.feat = feat; p.codes = codes.data(); p.env_flags = flags.data(); p.gps = gps; p.compass = compass; p.trig = trig; p.gmap = gmap;
   p.ego = ego_out; p.proj_out = proj_out; p.proj_in = (mode == 2) ? proj_in : nullptr;
   p.stop_after_scatter = (mode == 1); p.bs = d->bs; p.g = g; p.sp = sp; p.ego_half = ego_half; p.env_slots = env_slots;
+  p.n_maps = d->n_maps;
   std::vector<unsigned char> smem(sp.total + 128);
   unsigned char* sm = smem.data() + ((128 - ((uintptr_t)smem.data() & 127)) & 127);
   const int slabs = (g.C + SLAB - 1) / SLAB;

@@ -1,6 +1,6 @@
-"""Thin torch-tensor wrappers over the C ABI (include/wsmg.h).  Each function validates
-nothing beyond what it needs to build the call -- libwsmg validates dims/pointers and the
-error code is raised as WsmgError.  All work is enqueued on the current CUDA stream."""
+"""Thin torch-tensor wrappers over the C ABI (include/wsmg.h).  Each function checks that its tensors are what the
+raw pointers will be read as (device, dtype, contiguity) -- libwsmg validates dims/pointers and its error code is
+raised as WsmgError.  All work is enqueued on the current CUDA stream."""
 from __future__ import annotations
 
 import ctypes
@@ -16,6 +16,24 @@ def _ptr(t):
 
 def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _chk(t, name, device=None, dtype=torch.float32, numel=None, optional=False):
+    """The C ABI reads raw pointers: refuse anything it would misread."""
+    if t is None:
+        if optional:
+            return
+        raise ValueError(f"{name} is required")
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} has dtype {t.dtype}, expected {dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if numel is not None and t.numel() != numel:
+        raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
 
 
 def dims_for(feat_shape, depth_shape, n_maps, e=100, g=240, resolution=0.12, map_depth=None):
@@ -37,22 +55,40 @@ def alloc_scratch(dims, device):
 
 
 def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, trig=None, scratch=None, ego=None,
-               ego_half=None, env_slots=None):
+               ego_half=None, env_slots=None, status=None, events=None):
     """One step.  feat [bs,C,Hf,Wf], depth [bs,Hd,Wd,1], gmap [n,G,G,C] (updated in place).  Returns ego [bs,C,E,E].
     ego_half: optional fp16 [bs,C,E,E] tensor that receives the rounded copy (rollout store);
-    env_slots: optional int32 [bs] map row per frame (see include/wsmg.h wsmg_opts)."""
+    env_slots: optional int32 [bs] map row per frame; status: optional pinned int32[2] the kernels raise
+    (dropped pixels / bad slot); events: optional (before, after) torch.cuda.Event pair recorded around k_fused
+    (see include/wsmg.h wsmg_opts)."""
     lib = _lib.load()
+    if not gmap.is_cuda:
+        raise ValueError("gmap must be a CUDA tensor (no CPU fallback)")
     dev = gmap.device
+    bs = feat.shape[0]
+    _chk(gmap, "gmap", dev)
+    _chk(feat, "feat", dev)
+    _chk(depth, "depth", dev, numel=bs * depth.shape[1] * depth.shape[2])
+    _chk(gps, "gps", dev, numel=2 * bs)
+    _chk(compass, "compass", dev, numel=bs)
+    _chk(mask, "mask", dev, numel=bs)
+    _chk(trig, "trig", dev, numel=4 * bs, optional=True)
     d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution, map_depth=gmap.shape[3])
     if scratch is None:
         scratch = alloc_scratch(d, dev)
+    _chk(scratch, "scratch", dev, dtype=torch.uint8)
     if ego is None:
-        ego = torch.empty(feat.shape[0], gmap.shape[3], e, e, device=dev, dtype=torch.float32)
-    if ego_half is not None and (ego_half.dtype != torch.float16 or tuple(ego_half.shape) != tuple(ego.shape)):
-        raise ValueError("ego_half must be a float16 tensor shaped like the ego map")
-    if env_slots is not None and (env_slots.dtype != torch.int32 or env_slots.numel() != feat.shape[0]):
-        raise ValueError("env_slots must be int32 [bs]")
-    opts = _lib.WsmgOpts(_ptr(trig), _ptr(ego_half), _ptr(env_slots), None, None)
+        ego = torch.empty(bs, gmap.shape[3], e, e, device=dev, dtype=torch.float32)
+    _chk(ego, "ego", dev, numel=bs * gmap.shape[3] * e * e)
+    if ego_half is not None:
+        _chk(ego_half, "ego_half", dev, dtype=torch.float16, numel=ego.numel())
+    _chk(env_slots, "env_slots", dev, dtype=torch.int32, numel=bs, optional=True)
+    if status is not None and not (status.dtype == torch.int32 and status.numel() >= 2 and status.is_contiguous()
+                                   and (status.is_pinned() or status.device == dev)):
+        raise ValueError("status must be an int32[2] tensor in pinned host memory (or on the device)")
+    opts = _lib.WsmgOpts(_ptr(trig), _ptr(ego_half), _ptr(env_slots),
+                         None if events is None else ctypes.c_void_p(events[0].cuda_event),
+                         None if events is None else ctypes.c_void_p(events[1].cuda_event), _ptr(status))
     with torch.cuda.device(dev):
         rc = lib.wsmg_map_update_ex(_ptr(feat), _ptr(depth), _ptr(gps), _ptr(compass), _ptr(mask), _ptr(gmap), _ptr(ego),
                                     ctypes.byref(opts), _ptr(scratch), scratch.numel(), ctypes.byref(d), _stream(dev))
@@ -62,7 +98,7 @@ def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, tr
 
 def env_flags(scratch, dims):
     """Per-env status words of the last update that used `scratch` (synchronises): int32 [bs], bits
-    _lib.FLAG_INVALID_PIXEL / _lib.FLAG_OUTSIDE_FAN (see include/wsmg.h)."""
+    _lib.FLAG_INVALID_PIXEL / _lib.FLAG_OUTSIDE_FAN / _lib.FLAG_BAD_SLOT (see include/wsmg.h)."""
     off = int(_lib.load().wsmg_scratch_flags_offset(ctypes.byref(dims)))
     return scratch[off:off + 4 * dims.bs].view(torch.int32).cpu()
 
@@ -70,8 +106,11 @@ def env_flags(scratch, dims):
 def unproject_index(depth, hf, wf, e=100, g=240, resolution=0.12):
     """depth [bs,Hd,Wd,1] -> (lin int32 [bs,hf,wf], invalid bool [bs,hf,wf])."""
     lib = _lib.load()
+    if not depth.is_cuda:
+        raise ValueError("depth must be a CUDA tensor (no CPU fallback)")
     dev = depth.device
     bs = depth.shape[0]
+    _chk(depth, "depth", dev)
     d = _lib.make_dims(bs, bs, 4, hf, wf, depth.shape[1], depth.shape[2], e, g, resolution)
     lin = torch.empty(bs, hf, wf, dtype=torch.int32, device=dev)
     inv = torch.empty(bs, hf, wf, dtype=torch.uint8, device=dev)
@@ -84,7 +123,11 @@ def unproject_index(depth, hf, wf, e=100, g=240, resolution=0.12):
 def scatter_max(feat, depth, e=100, g=240, resolution=0.12, map_depth=None):
     """-> proj_feats [bs,C,E,E] (before rotation); map_depth != feat channels applies the fused channel pool."""
     lib = _lib.load()
+    if not feat.is_cuda:
+        raise ValueError("feat must be a CUDA tensor (no CPU fallback)")
     dev = feat.device
+    _chk(feat, "feat", dev)
+    _chk(depth, "depth", dev, numel=feat.shape[0] * depth.shape[1] * depth.shape[2])
     d = dims_for(feat.shape, depth.shape, feat.shape[0], e, g, resolution, map_depth=map_depth)
     scratch = alloc_scratch(d, dev)
     proj = torch.empty(feat.shape[0], d.C, e, e, device=dev, dtype=torch.float32)
@@ -96,14 +139,22 @@ def scatter_max(feat, depth, e=100, g=240, resolution=0.12, map_depth=None):
 
 
 def register_fuse_retrieve(proj, gps, compass, mask, gmap, resolution=0.12, trig=None):
+    """Everything after the projection.  proj [bs,C,E,E] must be zero outside the fan a depth >= 0 pixel can reach
+    (what scatter_max returns): cells outside it are ignored."""
     lib = _lib.load()
+    if not gmap.is_cuda:
+        raise ValueError("gmap must be a CUDA tensor (no CPU fallback)")
     dev = gmap.device
     bs, c, e, _ = proj.shape
+    for t, name, n in ((proj, "proj", None), (gmap, "gmap", None), (gps, "gps", 2 * bs), (compass, "compass", bs), (mask, "mask", bs)):
+        _chk(t, name, dev, numel=n)
+    _chk(trig, "trig", dev, numel=4 * bs, optional=True)
     d = _lib.make_dims(bs, gmap.shape[0], c, 4, 4, 4, 4, e, gmap.shape[1], resolution)
+    scratch = alloc_scratch(d, dev)
     ego = torch.empty(bs, c, e, e, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         rc = lib.wsmg_register_fuse_retrieve(_ptr(proj), _ptr(gps), _ptr(compass), _ptr(mask), _ptr(gmap), _ptr(ego),
-                                             _ptr(trig), ctypes.byref(d), _stream(dev))
+                                             _ptr(trig), _ptr(scratch), scratch.numel(), ctypes.byref(d), _stream(dev))
     _lib.check(rc, "wsmg_register_fuse_retrieve")
     return ego
 
@@ -159,6 +210,11 @@ class HostPipeline:
         self.staging = torch.empty(n, dtype=torch.uint8, device=self.device)
 
     def step(self, feat_h, depth_h, gps_h, compass_h, mask_h, gmap, ego_h):
+        bs = self.dims.bs
+        for t, name, n in ((feat_h, "feat_h", None), (depth_h, "depth_h", bs * self.dims.Hd * self.dims.Wd), (gps_h, "gps_h", 2 * bs),
+                           (compass_h, "compass_h", bs), (mask_h, "mask_h", bs), (ego_h, "ego_h", None)):
+            _chk(t, name, torch.device("cpu"), numel=n)
+        _chk(gmap, "gmap", self.device)
         with torch.cuda.device(self.device):
             rc = self.lib.wsmg_map_update_host_ex(_ptr(feat_h), _ptr(depth_h), _ptr(gps_h), _ptr(compass_h), _ptr(mask_h),
                                                   _ptr(gmap), _ptr(ego_h), _ptr(self.staging), self.staging.numel(),

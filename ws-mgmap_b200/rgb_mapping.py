@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import warnings
 
 import torch
 import torch.nn as nn
@@ -84,15 +85,59 @@ class Mapping(nn.Module):
             raise RuntimeError("wsmgmap_b200.Mapping needs a CUDA device (no CPU fallback)")
         self._lib = _lib.load()
         g, c = self.global_map_size, self.global_map_depth
+        self._env_slots = None
+        self._env_slots_host = None
         # caller-owned, re-bindable state: fetched from the attribute on every call
         self.full_global_map = torch.zeros(self.num_proc, g, g, c, device=self.device)
         self.agent_view = torch.zeros(self.num_proc, c, g, g, device=self.device)
         self._scratch = None
-        # Opt-in extras beyond the reference's contract; both default to the reference behaviour.
-        self.env_slots = None        # int32 [bs] CUDA tensor: frame b uses map row env_slots[b] (see pause_envs)
+        # Two status words in pinned (device-mapped) host memory that the kernels raise and forward() polls at the
+        # NEXT call without synchronising: [0] a valid pixel fell outside the fan and was dropped (depth < 0; the
+        # reference would scatter it), [1] an env slot was not a row of the map (include/wsmg.h wsmg_opts.status).
+        self._status = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self._status_np = self._status.numpy()
+        # Opt-in extras beyond the reference's contract; all default to the reference behaviour.
         self.store_half = False      # also emit an fp16 copy of the ego map into self.last_ego_half
         self.last_ego_half = None
         self.strict_inputs = False   # debugging aid: synchronise after each update and raise if a valid pixel was dropped
+
+    # -- caller-owned state with consistency checks -------------------------------------------
+    # `full_global_map` is re-bound by the trainers (zeros of a new leading size before a rollout,
+    # map[state_index] when envs are paused: common_trainer.py:171-172,266,429-435).  A slot table set through
+    # pause_envs()/env_slots refers to rows of the tensor it was made for: re-binding a tensor with another leading
+    # dimension drops it (the re-indexed tensor is already compact), so a stale table can never address rows that
+    # no longer exist.
+    @property
+    def full_global_map(self):
+        return self._full_global_map
+
+    @full_global_map.setter
+    def full_global_map(self, value):
+        old = getattr(self, "_full_global_map", None)
+        self._full_global_map = value
+        if self._env_slots is not None and (old is None or value.shape[0] != old.shape[0]):
+            warnings.warn("full_global_map was re-bound with a different number of rows: the env slot table set by "
+                          "pause_envs() is dropped (use either pause_envs() or the reference's re-indexing, not both)")
+            self._env_slots = self._env_slots_host = None
+
+    @property
+    def env_slots(self):
+        """int32 [bs] CUDA tensor: frame b reads / updates map row env_slots[b] (None: row b).  See pause_envs."""
+        return self._env_slots
+
+    @env_slots.setter
+    def env_slots(self, value):
+        if value is None:
+            self._env_slots = self._env_slots_host = None
+            return
+        n = self._full_global_map.shape[0]
+        host = [int(v) for v in (value.tolist() if isinstance(value, torch.Tensor) else value)]
+        if any(v < 0 or v >= n for v in host):
+            raise ValueError(f"env_slots {host} must be rows of full_global_map (0..{n - 1})")
+        if len(set(host)) != len(host):
+            raise ValueError(f"env_slots {host} must be distinct (two frames on one map row would race)")
+        self._env_slots_host = host
+        self._env_slots = torch.tensor(host, dtype=torch.int32, device=self._full_global_map.device)
 
     # -- helpers ---------------------------------------------------------------------------
     def _dims(self, bs, n_maps, hf, wf, hd, wd, c_in):
@@ -144,12 +189,16 @@ class Mapping(nn.Module):
             raise ValueError("gps must be [bs,2], compass [bs,1], masks [bs,1]")
         dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2], cf)
         scratch = self._scratch_for(dims, dev)
-        slots = self.env_slots
-        if slots is not None and slots.numel() != bs:
-            raise ValueError(f"env_slots has {slots.numel()} entries for a batch of {bs}")
+        slots = self._env_slots
+        if slots is not None:
+            if slots.numel() != bs:
+                raise ValueError(f"env_slots has {slots.numel()} entries for a batch of {bs}")
+            if slots.device != dev or max(self._env_slots_host) >= full_global_map.shape[0]:
+                raise ValueError("env_slots does not belong to this map tensor (device or row count differ)")
+        self._poll_status()
         half = torch.empty(bs, c, e, e, device=dev, dtype=torch.float16) if self.store_half else None
         ego = ops.map_update(features, depth, gps, compass, masks, full_global_map, e=e, resolution=self.resolution,
-                             trig=_trig, scratch=scratch, ego_half=half, env_slots=slots)
+                             trig=_trig, scratch=scratch, ego_half=half, env_slots=slots, status=self._status)
         self.last_ego_half = half
         if self.strict_inputs:
             flags = ops.env_flags(scratch, dims)
@@ -159,6 +208,20 @@ class Mapping(nn.Module):
                                  "(the reference would scatter them) -- see include/wsmg.h WSMG_FLAG_OUTSIDE_FAN")
         return ego, full_global_map
 
+    def _poll_status(self):
+        """What earlier updates reported through the pinned status words (no synchronisation: the kernels may still
+        be running, a report can arrive one call late)."""
+        st = self._status_np
+        if st[0] != 0:
+            st[0] = 0
+            warnings.warn("wsmgmap_b200: an earlier map update saw depth < 0 -- pixels behind the camera are DROPPED by "
+                          "the B200 kernel where the reference would scatter them (include/wsmg.h WSMG_FLAG_OUTSIDE_FAN); "
+                          "set strict_inputs=True to locate the frame", RuntimeWarning)
+        if st[1] != 0:
+            st[1] = 0
+            raise _lib.WsmgError("an earlier map update was given an env slot that is not a row of full_global_map: "
+                                 "that frame was skipped (include/wsmg.h WSMG_FLAG_BAD_SLOT)")
+
     # -- opt-in extras ---------------------------------------------------------------------
     def pause_envs(self, envs_to_pause):
         """O(1) replacement for the trainers' `full_global_map = full_global_map[state_index]`
@@ -166,10 +229,10 @@ class Mapping(nn.Module):
         envs from the slot table; the map tensor keeps its rows.  Batch element b then updates row
         env_slots[b].  Callers that use this must NOT also re-index full_global_map."""
         n = self.full_global_map.shape[0]
-        slots = list(range(n)) if self.env_slots is None else self.env_slots.tolist()
+        slots = list(range(n)) if self._env_slots_host is None else list(self._env_slots_host)
         for idx in sorted(envs_to_pause, reverse=True):
             slots.pop(idx)
-        self.env_slots = torch.tensor(slots, dtype=torch.int32, device=self.full_global_map.device)
+        self.env_slots = slots
         return self.env_slots
 
     def reset_slots(self):
