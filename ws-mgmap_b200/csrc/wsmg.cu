@@ -1,9 +1,9 @@
 // libwsmg.so -- WS-MGMap per-step map update for B200 (sm_100a).  C ABI in include/wsmg.h.
 //
-// Three launches per step, all on the caller's stream:
-//   k_reset   episode-reset mask over the whole NHWC map       (rgb_mapping.py:35); per-env rotation sines / cosines
-//             and column bounds
-//   k_cells   fused unproject + height-band test + bin + index  (rgb_mapping.py:153-176, 188-217)
+// Two launches per step, both on the caller's stream, the second a programmatic dependent launch of the first:
+//   k_cells   fused unproject + height-band test + bin + index  (rgb_mapping.py:153-176, 188-217); its trailing blocks
+//             apply the episode-reset mask to the NHWC map (rgb_mapping.py:35) and evaluate the per-env rotation
+//             sines / cosines and column bounds (k_reset does the same for the stage entry points)
 //   k_fused   one CTA per (env, 4-channel slab): shared-memory scatter-max, rotate, translate,
 //             max-fuse into the map window, translate back, crop, rotate -> NCHW ego map
 //             (rgb_mapping.py:210-232, 37-70).  Body in wsmg_body.h.
@@ -23,42 +23,22 @@ namespace wsmg {
 
 constexpr int CELLS_THREADS = 256;
 
-// ------------------------------------------------------------------ k_reset
-// Per-env preparation, grid (bs, chunks):
-//   * full_global_map[:bs] *= masks (rgb_mapping.py:35); mask == 1 (the steady state) touches nothing;
-//   * clears the env flags (k_cells, the next launch, sets them);
-//   * once per env: both rotations' cos / sin exactly as the rotations will use them, and the per-row column bounds
-//     outside which the first rotation cannot see the fan (rot_row_bounds, wsmg_body.h);
-//   * flags an env slot that is not a row of the map tensor (the frame is then skipped everywhere).
-__global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
-                                               size_t per_env, uint32_t* __restrict__ env_flags,
-                                               const int32_t* __restrict__ env_slots, int32_t* __restrict__ row_bounds,
-                                               float* __restrict__ env_trig, const float* __restrict__ compass,
-                                               const float* __restrict__ trig, uint32_t* __restrict__ status, int n_maps, Geo g) {
-  const int b = blockIdx.x, chunk = blockIdx.y;
-  const int mrow = env_slots != nullptr ? env_slots[b] : b;
-  const bool bad_slot = gmap != nullptr && (unsigned)mrow >= (unsigned)n_maps;
-  if (chunk == 0 && threadIdx.x == 0) {
-    if (env_flags != nullptr) env_flags[b] = bad_slot ? WSMG_FLAG_BAD_SLOT : 0u;
-    if (bad_slot && status != nullptr) status[1] = 1u;
-  }
-  if (row_bounds != nullptr && chunk == gridDim.y - 1) {
-    float cs, sn;
-    if (trig != nullptr) { cs = trig[4 * b + 0]; sn = trig[4 * b + 1]; }
-    else { const float h = -compass[b]; sn = sinf(h); cs = cosf(h); }
-    for (int t = threadIdx.x; t < g.E; t += blockDim.x) row_bounds[(size_t)b * g.E + t] = rot_row_bounds(g, cs, sn, t);
-    if (env_trig != nullptr && threadIdx.x == 0) {             // both rotations' cos / sin, exactly as k_fused would evaluate them
-      float cs2, sn2;
-      if (trig != nullptr) { cs2 = trig[4 * b + 2]; sn2 = trig[4 * b + 3]; }
-      else { const float h = compass[b]; sn2 = sinf(h); cs2 = cosf(h); }
-      env_trig[4 * b + 0] = cs; env_trig[4 * b + 1] = sn; env_trig[4 * b + 2] = cs2; env_trig[4 * b + 3] = sn2;
-    }
-  }
-  if (gmap == nullptr || bad_slot) return;
-  const float m = mask[b];
-  if (m == 1.0f) return;
-  float* base = gmap + (size_t)mrow * per_env;
-  const size_t stride = (size_t)gridDim.y * blockDim.x;
+// ------------------------------------------------------------------ per-env preparation shared by k_reset and k_cells
+// In the whole-step launch (`pre.cell_blocks > 0`) the grid carries, per env, 1 + PRE_RESET_BLOCKS more blocks that do what
+// k_reset does for the stage entry points -- the rotations' cos / sin and column bounds, the bad-slot check, the
+// episode-reset mask -- so that a step is two launches, and every block leaves its flags in a word of its own
+// (block_flags[b][blk], plain store: nothing to clear beforehand); k_fused ORs the env's words.
+constexpr int PRE_RESET_BLOCKS = 16;
+struct PreArgs {
+  int cell_blocks = 0;             // > 0: whole-step launch with the extra roles below
+  uint32_t* block_flags = nullptr; // [bs][cell_blocks + 1]
+  float* gmap = nullptr; const float* mask = nullptr; size_t per_env = 0; const int32_t* env_slots = nullptr;
+  int32_t* row_bounds = nullptr; float* env_trig = nullptr; const float* compass = nullptr; const float* trig = nullptr;
+  int n_maps = 0;
+};
+
+__device__ __forceinline__ void reset_map_rows(float* __restrict__ base, float m, size_t per_env, int chunk, int chunks) {
+  const size_t stride = (size_t)chunks * blockDim.x;
   size_t i = (size_t)chunk * blockDim.x + threadIdx.x;
   if ((per_env & 3) == 0) {
     float4* b4 = reinterpret_cast<float4*>(base);
@@ -78,6 +58,46 @@ __global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const f
   }
 }
 
+// both rotations' cos / sin exactly as k_fused would evaluate them, and the first rotation's per-row column bounds
+__device__ __forceinline__ void env_rotation_setup(int b, const Geo& g, const float* __restrict__ compass, const float* __restrict__ trig,
+                                                   int32_t* __restrict__ row_bounds, float* __restrict__ env_trig) {
+  float cs, sn;
+  if (trig != nullptr) { cs = trig[4 * b + 0]; sn = trig[4 * b + 1]; }
+  else { const float h = -compass[b]; sn = sinf(h); cs = cosf(h); }
+  for (int t = threadIdx.x; t < g.E; t += blockDim.x) row_bounds[(size_t)b * g.E + t] = rot_row_bounds(g, cs, sn, t);
+  if (env_trig != nullptr && threadIdx.x == 0) {
+    float cs2, sn2;
+    if (trig != nullptr) { cs2 = trig[4 * b + 2]; sn2 = trig[4 * b + 3]; }
+    else { const float h = compass[b]; sn2 = sinf(h); cs2 = cosf(h); }
+    env_trig[4 * b + 0] = cs; env_trig[4 * b + 1] = sn; env_trig[4 * b + 2] = cs2; env_trig[4 * b + 3] = sn2;
+  }
+}
+
+// ------------------------------------------------------------------ k_reset
+// Per-env preparation for the STAGE entry points (the whole step folds it into the k_cells launch), grid (bs, chunks):
+//   * full_global_map[:bs] *= masks (rgb_mapping.py:35); mask == 1 (the steady state) touches nothing;
+//   * clears the env flags (k_cells, the next launch, sets them);
+//   * once per env: both rotations' cos / sin exactly as the rotations will use them, and the per-row column bounds
+//     outside which the first rotation cannot see the fan (rot_row_bounds, wsmg_body.h);
+//   * flags an env slot that is not a row of the map tensor (the frame is then skipped everywhere).
+__global__ void __launch_bounds__(256) k_reset(float* __restrict__ gmap, const float* __restrict__ mask,
+                                               size_t per_env, uint32_t* __restrict__ env_flags,
+                                               const int32_t* __restrict__ env_slots, int32_t* __restrict__ row_bounds,
+                                               float* __restrict__ env_trig, const float* __restrict__ compass,
+                                               const float* __restrict__ trig, uint32_t* __restrict__ status, int n_maps, Geo g) {
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int mrow = env_slots != nullptr ? env_slots[b] : b;
+  const bool bad_slot = gmap != nullptr && (unsigned)mrow >= (unsigned)n_maps;
+  if (chunk == 0 && threadIdx.x == 0) {
+    if (env_flags != nullptr) env_flags[b] = bad_slot ? WSMG_FLAG_BAD_SLOT : 0u;
+    if (bad_slot && status != nullptr) status[1] = 1u;
+  }
+  if (row_bounds != nullptr && chunk == gridDim.y - 1) env_rotation_setup(b, g, compass, trig, row_bounds, env_trig);
+  if (gmap == nullptr || bad_slot) return;
+  const float m = mask[b];
+  if (m != 1.0f) reset_map_rows(gmap + (size_t)mrow * per_env, m, per_env, chunk, gridDim.y);
+}
+
 // ------------------------------------------------------------------ k_cells
 // Fused unproject + height-band test + bin + index.  Each thread owns four consecutive sampled pixels
 // of the Hf x Wf frame (one 8-byte store of packed fan codes).  The depth rows a block needs are one
@@ -93,7 +113,27 @@ constexpr int CELLS_MAX_W = 1024;
 template <bool STAGE_API>
 __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict__ depth, uint16_t* __restrict__ codes,
                                                           int32_t* __restrict__ lin, uint8_t* __restrict__ invalid,
-                                                          uint32_t* __restrict__ env_flags, uint32_t* __restrict__ status, Geo g, int stage_rows) {
+                                                          uint32_t* __restrict__ env_flags, uint32_t* __restrict__ status, Geo g, int stage_rows,
+                                                          const PreArgs pre) {
+  // k_fused is launched with programmatic stream serialization behind this kernel: let its CTAs be scheduled as soon as
+  // every block of this grid has started (they wait for this grid's completion before touching what it writes)
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  if (pre.cell_blocks > 0 && (int)blockIdx.y >= pre.cell_blocks) {
+    const int b = blockIdx.x, role = (int)blockIdx.y - pre.cell_blocks;
+    const int mrow = pre.env_slots != nullptr ? pre.env_slots[b] : b;
+    const bool bad_slot = (unsigned)mrow >= (unsigned)pre.n_maps;
+    if (role == 0) {
+      if (threadIdx.x == 0) {
+        pre.block_flags[(size_t)b * (pre.cell_blocks + 1) + pre.cell_blocks] = bad_slot ? WSMG_FLAG_BAD_SLOT : 0u;
+        if (bad_slot && status != nullptr) status[1] = 1u;
+      }
+      env_rotation_setup(b, g, pre.compass, pre.trig, pre.row_bounds, pre.env_trig);
+    } else if (!bad_slot) {
+      const float m = pre.mask[b];
+      if (m != 1.0f) reset_map_rows(pre.gmap + (size_t)mrow * pre.per_env, m, pre.per_env, role - 1, PRE_RESET_BLOCKS);
+    }
+    return;
+  }
   extern __shared__ __align__(128) unsigned char cells_smem[];
   __shared__ int rowoff[160];
   __shared__ __align__(16) int col_src[CELLS_MAX_W];
@@ -180,8 +220,17 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
   }
   const unsigned bad = __ballot_sync(0xFFFFFFFFu, any_bad);
   const unsigned outl = __ballot_sync(0xFFFFFFFFu, any_outlier);
-  if (env_flags != nullptr && (bad | outl) != 0u && (threadIdx.x & 31) == 0)
-    atomicOr(env_flags + b, (bad ? WSMG_FLAG_INVALID_PIXEL : 0u) | (outl ? WSMG_FLAG_OUTSIDE_FAN : 0u));
+  const uint32_t word = (bad ? WSMG_FLAG_INVALID_PIXEL : 0u) | (outl ? WSMG_FLAG_OUTSIDE_FAN : 0u);
+  if (pre.cell_blocks > 0) {                                 // whole-step launch: this block's own word
+    __shared__ uint32_t blk_word;
+    if (threadIdx.x == 0) blk_word = 0u;
+    __syncthreads();
+    if (word != 0u && (threadIdx.x & 31) == 0) atomicOr(&blk_word, word);
+    __syncthreads();
+    if (threadIdx.x == 0) pre.block_flags[(size_t)b * (pre.cell_blocks + 1) + blockIdx.y] = blk_word;
+  } else if (env_flags != nullptr && word != 0u && (threadIdx.x & 31) == 0) {
+    atomicOr(env_flags + b, word);
+  }
   if (status != nullptr && outl != 0u && (threadIdx.x & 31) == 0) status[0] = 1u;   // sticky, polled by the host at its next call
 }
 
@@ -249,20 +298,28 @@ static int launch_reset(float* gmap, const float* mask, const wsmg_dims* d, cuda
   return (int)cudaGetLastError();
 }
 
-static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, uint32_t* env_flags,
-                        uint32_t* status, const Geo& g, int bs, cudaStream_t s) {
-  if (g.fan_rows > 160 || g.Wf > CELLS_MAX_W) return WSMG_E_DIMS;
-  const int HW = g.Hf * g.Wf;
+static int cell_blocks_of(const Geo& g) {
   const int per_block = CELLS_THREADS * CELLS_PX * CELLS_GROUPS;
-  dim3 grid(bs, (HW + per_block - 1) / per_block);
+  return (g.Hf * g.Wf + per_block - 1) / per_block;
+}
+
+// `pre` != nullptr: the whole-step launch (extra per-env blocks, per-block flag words; pre->cell_blocks is filled here).
+static int launch_cells(const float* depth, uint16_t* codes, int32_t* lin, uint8_t* invalid, uint32_t* env_flags,
+                        uint32_t* status, const Geo& g, int bs, cudaStream_t s, PreArgs* pre = nullptr) {
+  if (g.fan_rows > 160 || g.Wf > CELLS_MAX_W) return WSMG_E_DIMS;
+  const int per_block = CELLS_THREADS * CELLS_PX * CELLS_GROUPS;
+  const int cell_blocks = cell_blocks_of(g);
+  PreArgs pa;
+  if (pre != nullptr) { pre->cell_blocks = cell_blocks; pa = *pre; }
+  dim3 grid(bs, cell_blocks + (pre != nullptr ? 1 + PRE_RESET_BLOCKS : 0));
   if (grid.y > 65535u) return WSMG_E_DIMS;
   // depth rows one block can touch: its sampled rows (per_block / Wf + 2) times the subsampling ratio, + 1
   int stage_rows = (int)((per_block / g.Wf + 2) * (double)g.Hd / g.Hf) + 2;
   size_t smem = (size_t)stage_rows * g.Wd * 4;
   const bool bulk_ok = (g.Wd % 4) == 0 && (((size_t)g.Hd * g.Wd) % 4) == 0 && (reinterpret_cast<uintptr_t>(depth) & 15u) == 0;
   if (smem > 32 * 1024 || !bulk_ok) { stage_rows = 0; smem = 0; }     // fall back to direct global gathers
-  if (lin != nullptr || invalid != nullptr) k_cells<true><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, status, g, stage_rows);
-  else k_cells<false><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, status, g, stage_rows);
+  if (lin != nullptr || invalid != nullptr) k_cells<true><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, status, g, stage_rows, pa);
+  else k_cells<false><<<grid, CELLS_THREADS, smem, s>>>(depth, codes, lin, invalid, env_flags, status, g, stage_rows, pa);
   return (int)cudaGetLastError();
 }
 
@@ -343,18 +400,29 @@ static Switches switches() {
 }
 
 template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL = false>
-static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s, int dev) {
+static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s, int dev, bool pdl) {
   static int attr_set_for[64] = {0};          // dynamic shared memory opt-in, once per device and size
   if (attr_set_for[dev] < p.sp.total) {
     cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
     if (e != cudaSuccess) return (int)e;
     attr_set_for[dev] = p.sp.total;
   }
-  k_fused<CE, CG, CHW, VEC, TMA, POOL><<<grid, FUSED_NT, p.sp.total, s>>>(p);
-  return (int)cudaGetLastError();
+  if (!pdl) {
+    k_fused<CE, CG, CHW, VEC, TMA, POOL><<<grid, FUSED_NT, p.sp.total, s>>>(p);
+    return (int)cudaGetLastError();
+  }
+  // Programmatic dependent launch behind k_cells: the CTAs are scheduled while k_cells' last blocks drain and run their
+  // prologue (tables, key planes, pose) up to griddepcontrol.wait.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FUSED_NT); cfg.dynamicSmemBytes = (size_t)p.sp.total; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, k_fused<CE, CG, CHW, VEC, TMA, POOL>, p);
 }
 
-static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s) {
+static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s, bool pdl = false) {
   p.sp = geo_plan(d).sp;
   DeviceInfo di;
   int rc = device_info(&di);
@@ -374,19 +442,19 @@ static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s) {
     if (rc != 0) return rc;
   }
   if (p.g.Cin != p.g.C) {                                   // channel pool fused in the scatter: run-time geometry builds
-    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s, di.dev) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s, di.dev);
-    return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s, di.dev);
+    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s, di.dev, pdl);
+    return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s, di.dev, pdl);
   }
   const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !sw.generic;
   if (ref_geo && p.g.Hf * p.g.Wf == 224 * 224) {          // the reference's shapes (vlnce_task.yaml:11-18)
-    return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s, di.dev)
-               : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s, di.dev);
+    return tma ? launch_fused_t<100, 240, 224 * 224, true, true>(p, grid, s, di.dev, pdl)
+               : launch_fused_t<100, 240, 224 * 224, true, false>(p, grid, s, di.dev, pdl);
   }
   if (ref_geo && p.g.Hf * p.g.Wf == 256 * 256 && tma) {   // BASELINE.json's wording: features at the depth resolution
-    return launch_fused_t<100, 240, 256 * 256, true, true>(p, grid, s, di.dev);
+    return launch_fused_t<100, 240, 256 * 256, true, true>(p, grid, s, di.dev, pdl);
   }
-  if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s, di.dev) : launch_fused_t<0, 0, 0, true, false>(p, grid, s, di.dev);
-  return launch_fused_t<0, 0, 0, false, false>(p, grid, s, di.dev);
+  if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false>(p, grid, s, di.dev, pdl);
+  return launch_fused_t<0, 0, 0, false, false>(p, grid, s, di.dev, pdl);
 }
 
 }  // namespace wsmg
@@ -434,21 +502,21 @@ static int map_update_impl(const float* feat, const float* depth, const float* g
   if (scratch_bytes_ < scratch_bytes(d)) return WSMG_E_SCRATCH;
   const Geo& g = geo_plan(d).g;
   const ScratchView sv = scratch_view(scratch, d);
-  ResetArgs ra;
-  ra.env_flags = sv.flags; ra.env_slots = o->env_slots; ra.row_bounds = sv.bounds;
-  ra.env_trig = sv.env_trig; ra.compass = compass; ra.trig = o->trig; ra.status = o->status;
-  rc = launch_reset(gmap, mask, d, s, ra);
-  if (rc) return rc;
-  rc = launch_cells(depth, sv.codes, nullptr, nullptr, sv.flags, o->status, g, d->bs, s);
+  PreArgs pre;
+  pre.block_flags = sv.block_flags; pre.gmap = gmap; pre.mask = mask; pre.per_env = (size_t)d->G * d->G * d->C;
+  pre.env_slots = o->env_slots; pre.row_bounds = sv.bounds; pre.env_trig = sv.env_trig; pre.compass = compass; pre.trig = o->trig;
+  pre.n_maps = d->n_maps;
+  rc = launch_cells(depth, sv.codes, nullptr, nullptr, nullptr, o->status, g, d->bs, s, &pre);
   if (rc) return rc;
   FusedParams p{};
   p.row_bounds = sv.bounds; p.env_trig = sv.env_trig; p.status = o->status;
+  p.block_flags = sv.block_flags; p.flag_words = pre.cell_blocks + 1; p.env_flags_out = sv.flags;
   p.feat = feat; p.codes = sv.codes; p.env_flags = sv.flags; p.gps = gps; p.compass = compass; p.trig = o->trig;
   p.gmap = gmap; p.ego = ego_out; p.proj_out = nullptr; p.proj_in = nullptr;
   p.ego_half = (uint16_t*)o->ego_half; p.env_slots = o->env_slots;
   p.stop_after_scatter = 0; p.bs = d->bs; p.g = g;
   if (o->ev_before_fused) cudaEventRecord((cudaEvent_t)o->ev_before_fused, s);
-  rc = launch_fused(p, d, s);
+  rc = launch_fused(p, d, s, /*pdl=*/o->ev_before_fused == nullptr);   // (an event between the two launches would serialise them anyway)
   if (o->ev_after_fused) cudaEventRecord((cudaEvent_t)o->ev_after_fused, s);
   return rc;
 }

@@ -123,7 +123,10 @@ struct TensorMapBlob { unsigned char bytes[8]; };
 
 struct FusedParams {
   TensorMapBlob tmap;       // [n_maps,G,G,C] fp32, box {4, WWP, TMA_ROWS, 1}; filled for the TMA builds
-  const uint32_t* env_flags; // [bs] bit0: the env has at least one pixel that does not write (k_cells)
+  const uint32_t* env_flags; // [bs] bit0: the env has at least one pixel that does not write (k_cells, stage entry points)
+  const uint32_t* block_flags; // whole step: [bs][flag_words] one word per k_cells block of the env (null: env_flags holds the OR)
+  uint32_t* env_flags_out;  // whole step: [bs] receives the OR of the env's block words (written by the env's first slab CTA)
+  int flag_words;
   const float* feat;        // [bs,C,Hf,Wf]
   const uint16_t* codes;    // [bs,Hf*Wf] packed fan codes from k_cells
   const float* gps;         // [bs,2]
@@ -153,6 +156,7 @@ __device__ __forceinline__ void smem_max(int32_t* a, int32_t v) { atomicMax(a, v
 __device__ __forceinline__ bool warp_all_nonneg(int32_t bits) { return __ballot_sync(__activemask(), bits < 0) == 0u; }
 __device__ __forceinline__ uint2 ld_codes(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void async_copy16(void* dst_smem, const void* src, bool pred) {
   unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
   int n = pred ? 16 : 0;   // src-size 0 => 16 bytes of zero fill, src not read
@@ -194,6 +198,7 @@ inline void smem_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
 inline bool warp_all_nonneg(int32_t bits) { return bits >= 0; }
 inline uint2 ld_codes(const uint2* p) { return *p; }
 inline void st_stream(float* p, float v) { *p = v; }
+inline void grid_dependency_wait() {}
 inline void async_copy16(void* dst, const void* src, bool pred) {
   if (pred) __builtin_memcpy(dst, src, 16); else __builtin_memset(dst, 0, 16);
 }
@@ -343,6 +348,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float* scal = reinterpret_cast<float*>(bars + MAX_BANDS);   // {cos, sin}(-compass), {cos, sin}(+compass), env flags
   int32_t* hitrow = reinterpret_cast<int32_t*>(scal + 8);      // per R row: first | (last + 1) << 16 column that can see the fan
   if (WSMG_SKIP(4096)) return;
+  // Launched as a programmatic dependent of k_cells: everything below reads what that grid (and k_reset before it)
+  // wrote -- codes, flags, rotation tables, the reset map.  A no-op for a plain launch.
+  grid_dependency_wait();
 
   // ---- per-env scalars that later phases need: fetched and evaluated now by three lanes of three different
   // warps, parked in shared memory -- their global-memory latency would otherwise stall the whole CTA right
@@ -365,7 +373,16 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         scal[2] = cs_; scal[3] = sn_;
       }
     }
-    if (tid == t_fl && p.proj_in == nullptr) scal[4] = as_float((int)p.env_flags[b]);
+    if (tid == t_fl && p.proj_in == nullptr) {
+      uint32_t fl = 0u;
+      if (p.block_flags != nullptr) {
+        for (int w = 0; w < p.flag_words; ++w) fl |= p.block_flags[(size_t)b * p.flag_words + w];
+        if (block % ((C + SLAB - 1) / SLAB) == 0) p.env_flags_out[b] = fl;      // per-env summary (include/wsmg.h: wsmg_scratch_flags_offset)
+      } else {
+        fl = p.env_flags[b];
+      }
+      scal[4] = as_float((int)fl);
+    }
   }
 
   // ---- pose scalars (every thread, redundantly) ------------------- rgb_mapping.py:34,45-51,57-63

@@ -19,6 +19,7 @@ inline int validate_dims(const wsmg_dims* d) {
   if (d->n_maps < d->bs) return WSMG_E_BATCH;
   if (d->C_in < 0) return WSMG_E_CHANNELS;
   if ((d->Hf * d->Wf) % 4 != 0) return WSMG_E_ALIGN;
+  if ((long long)d->Hf * d->Wf > 63LL * 2048) return WSMG_E_DIMS;   // per-block flag words of the k_cells launch (wsmg_host.h MAX_FLAG_WORDS)
   if (d->E > 126 || d->G > 32768) return WSMG_E_DIMS;          // 16-bit fan codes; (E+2)/8 bands must fit the barrier array; row tables of 128
   return WSMG_OK;
 }
@@ -68,25 +69,28 @@ inline const char* error_string(int code) {
 }
 
 // scratch layout: [bs * Hf*Wf] uint16 packed cell codes | [bs] uint32 env flags | [bs * E] int32 rotation column bounds |
-// [bs * 4] fp32 rotation sines / cosines
+// [bs * 4] fp32 rotation sines / cosines | [bs * 64] uint32 per-block flag words of the k_cells launch
 inline size_t pad256(size_t n) { return (n + 255) & ~(size_t)255; }
 inline size_t scratch_codes_bytes(const wsmg_dims* d) { return pad256((size_t)d->bs * d->Hf * d->Wf * sizeof(uint16_t)); }
 inline size_t scratch_flags_bytes(const wsmg_dims* d) { return pad256((size_t)d->bs * sizeof(uint32_t)); }
 inline size_t scratch_bounds_bytes(const wsmg_dims* d) { return pad256((size_t)d->bs * d->E * sizeof(int32_t)); }
 inline size_t scratch_trig_bytes(const wsmg_dims* d) { return pad256((size_t)d->bs * 4 * sizeof(float)); }
+constexpr int MAX_FLAG_WORDS = 64;       // k_cells blocks per env + 1 (validated: Hf*Wf <= 63 * 2048)
+inline size_t scratch_blockflags_bytes(const wsmg_dims* d) { return pad256((size_t)d->bs * MAX_FLAG_WORDS * sizeof(uint32_t)); }
 inline size_t scratch_bytes(const wsmg_dims* d) {
-  return scratch_codes_bytes(d) + scratch_flags_bytes(d) + scratch_bounds_bytes(d) + scratch_trig_bytes(d);
+  return scratch_codes_bytes(d) + scratch_flags_bytes(d) + scratch_bounds_bytes(d) + scratch_trig_bytes(d) + scratch_blockflags_bytes(d);
 }
 
 // Views into a scratch buffer.
-struct ScratchView { uint16_t* codes; uint32_t* flags; int32_t* bounds; float* env_trig; };
+struct ScratchView { uint16_t* codes; uint32_t* flags; int32_t* bounds; float* env_trig; uint32_t* block_flags; };
 inline ScratchView scratch_view(void* scratch, const wsmg_dims* d) {
   unsigned char* p = (unsigned char*)scratch;
   ScratchView v;
   v.codes = (uint16_t*)p; p += scratch_codes_bytes(d);
   v.flags = (uint32_t*)p; p += scratch_flags_bytes(d);
   v.bounds = (int32_t*)p; p += scratch_bounds_bytes(d);
-  v.env_trig = (float*)p;
+  v.env_trig = (float*)p; p += scratch_trig_bytes(d);
+  v.block_flags = (uint32_t*)p;
   return v;
 }
 
