@@ -238,7 +238,7 @@ def workload_config(args, world):
     return {"workload": f"{args.workload}: {total} envs in total, {per_gpu} per GPU ({scaling} scaling), env-sharded, "
                         f"C={SHAPE['C']} feat {SHAPE['Hf']}x{SHAPE['Wf']} depth {SHAPE['Hd']}x{SHAPE['Wd']} ego 100 global 240 fp32, depth kinds mixed "
                         f"{'/'.join(DEPTH_KINDS)}, random-walk poses, a new frame per env per step, masks=1 after the first step",
-            "envs_total": total, "envs_per_gpu": per_gpu, "scaling": scaling,
+            "envs_total": total, "envs_per_gpu": per_gpu, "scaling": scaling, "feat_layout": getattr(args, "feat_layout", "nchw"),
             "l2": "inputs larger than L2 (no flush)" if per_gpu >= 64 else "L2 flushed between steps",
             "bytes_per_frame_algorithmic": algorithmic_bytes_per_frame()}
 
@@ -247,7 +247,7 @@ def workload_config(args, world):
 class Resident:
     """`n` envs of the workload resident in HBM and the step that updates them."""
 
-    def __init__(self, n, T, dev, rank, lib):
+    def __init__(self, n, T, dev, rank, lib, nhwc=False):
         import torch
         import wsmgmap_b200  # noqa: F401
         from wsmgmap_b200 import ops
@@ -258,7 +258,11 @@ class Resident:
         # Every env sees a NEW frame every step, as in a rollout: n + T frames are resident and step t reads the
         # window [t, t+n).  (Re-feeding the same frame would leave the max-fused map unchanged after a few steps,
         # and a map update that changes nothing also writes nothing.)
-        self.feat_all = torch.rand(n + T, s["C"], s["Hf"], s["Wf"], generator=gen, device=dev)
+        self.nhwc = nhwc
+        if nhwc:      # channels_last producer: [frames, Hf, Wf, C] in memory (wsmg_dims.feat_nhwc)
+            self.feat_all = torch.rand(n + T, s["Hf"], s["Wf"], s["C"], generator=gen, device=dev)
+        else:
+            self.feat_all = torch.rand(n + T, s["C"], s["Hf"], s["Wf"], generator=gen, device=dev)
         cgen = torch.Generator().manual_seed(99 + rank)
         kinds = [make_depth(k, 8, s["Hd"], s["Wd"], cgen) for k in DEPTH_KINDS]
         self.depth_all = torch.stack([kinds[b % 4][(b // 4) % 8] for b in range(n + T)], 0).to(dev).contiguous()
@@ -269,7 +273,7 @@ class Resident:
         self.masks = torch.stack([p[2] for p in poses]).to(dev)
         self.gmap = torch.zeros(n, s["G"], s["G"], s["C"], device=dev)
         self.ego = torch.empty(n, s["C"], s["E"], s["E"], device=dev)
-        self.d = ops.dims_for((n, s["C"], s["Hf"], s["Wf"]), (n, s["Hd"], s["Wd"], 1), n, s["E"], s["G"], s["resolution"])
+        self.d = ops.dims_for((n, s["C"], s["Hf"], s["Wf"]), (n, s["Hd"], s["Wd"], 1), n, s["E"], s["G"], s["resolution"], feat_nhwc=nhwc)
         self.scratch = ops.alloc_scratch(self.d, dev)
         self.stream = torch.cuda.current_stream(dev)
 
@@ -455,7 +459,7 @@ def run_native(args, rank, local_rank, world):
 
     # ---- device-resident throughput (`value`) and the dominant kernel alone (roofline) --------------------
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if n < 64 else None
-    res = Resident(n, T, dev, rank, lib)
+    res = Resident(n, T, dev, rank, lib, nhwc=args.feat_layout == "nhwc")
     with ClockSampler(local_rank) as clk:
         elapsed_ms, fused_ms, checksum = time_resident(res, K, W, barrier, flush_buf)
 
@@ -640,6 +644,8 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling variant at N > 1")
     ap.add_argument("--no-small-batch", action="store_true", help="skip the env8 sub-record")
     ap.add_argument("--no-policy", action="store_true", help="skip the policy-forward record")
+    ap.add_argument("--feat-layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="memory layout of the resident feature tensor (nhwc: a channels_last producer, consumed without a permute copy)")
     ap.add_argument("--shape", default="real", choices=sorted(SHAPES), help="tensor shapes (secondary shapes of SURVEY 8d)")
     args = ap.parse_args()
     SHAPE.clear()

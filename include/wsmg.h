@@ -54,6 +54,10 @@ typedef struct wsmg_dims {
                       RGBMapping.forward (adaptive_max_pool1d over channels, rgb_mapping.py:81-84)
                       is applied inside the scatter: output channel k = max over input channels
                       [floor(k*C_in/C), ceil((k+1)*C_in/C)).                       */
+  int32_t feat_nhwc; /* 0: `feat` is [bs,C,Hf,Wf] (NCHW, what unet_encoder.py:103-111 returns by default);
+                      1: `feat` is [bs,Hf,Wf,C] in memory -- a torch channels_last tensor, the layout cuDNN's NHWC
+                      convolutions produce -- and is consumed as it is, no permute copy.  Needs C % 4 == 0 and
+                      C_in == 0 / C (no channel re-binning).                        */
 } wsmg_dims;
 
 int wsmg_abi_version(void);
@@ -85,7 +89,8 @@ size_t wsmg_scratch_flags_offset(const wsmg_dims* d);
 
 /* Whole step: Mapping.project_feat_to_map (rgb_mapping.py:32-72) as called by
  * RGBMapping.forward (rgb_mapping.py:85).
- *   feat     [bs,C_in,Hf,Wf] fp32 NCHW       (rgb_features as the UNet emits them; channel pool of :81-84 fused)
+ *   feat     [bs,C_in,Hf,Wf] fp32 NCHW       (rgb_features as the UNet emits them; channel pool of :81-84 fused),
+ *            or [bs,Hf,Wf,C] when wsmg_dims.feat_nhwc is set (channels_last producer)
  *   depth    [bs,Hd,Wd,1] fp32 in [0,1]      (observations['depth']; the x10 of :37 is applied inside)
  *   gps      [bs,2], compass [bs,1], mask [bs,1] fp32
  *   gmap     [n_maps,G,G,C] fp32 NHWC        (self.full_global_map; rows [:bs] updated in place, :35,:56)

@@ -41,13 +41,16 @@ def emul_cells(depth, hf, e=100, g=240, res=0.12):
 
 
 def emul_step(gmap, feat, depth, gps, compass, masks, trig=None, mode=0, proj_in=None, want_proj=False, e=100, g=240, res=0.12,
-              ego_half=None, env_slots=None, map_depth=None):
+              ego_half=None, env_slots=None, map_depth=None, feat_nhwc=False):
     """gmap [n,G,G,C] updated in place.  trig [bs,4] or None.  Returns (ego, proj or None).
     ego_half: optional uint16 array [bs,C,E,E] receiving the fp16 bits; env_slots: optional int32 [bs]."""
     bs, c_in, hf, wf = feat.shape if feat is not None else (proj_in.shape[0], proj_in.shape[1], 4, 4)
     c = c_in if map_depth is None else map_depth
     hd, wd = (depth.shape[1], depth.shape[2]) if depth is not None else (4, 4)
-    d = make_dims(bs, gmap.shape[0] if gmap is not None else bs, c, hf, wf, hd, wd, e, g, res, c_in=0 if c == c_in else c_in)
+    d = make_dims(bs, gmap.shape[0] if gmap is not None else bs, c, hf, wf, hd, wd, e, g, res, c_in=0 if c == c_in else c_in,
+                  feat_nhwc=1 if feat_nhwc else 0)
+    if feat_nhwc:                                   # logical NCHW array in, NHWC memory to the kernel body
+        feat = np.ascontiguousarray(np.transpose(feat, (0, 2, 3, 1)))
     ego = np.zeros((bs, c, e, e), np.float32)
     proj = np.zeros((bs, c, e, e), np.float32) if (want_proj or mode == 1) else None
     arrs = [None if a is None else np.ascontiguousarray(a, np.float32) for a in (feat, depth, gps, compass, masks)]

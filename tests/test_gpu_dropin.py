@@ -94,6 +94,42 @@ def test_channel_rebinning_and_input_checks():
         m(feat.to(DEV), dict(depth=depth, gps=obs["gps"], compass=obs["compass"]), torch.zeros(2, 1, device=DEV))  # CPU depth
 
 
+def test_channels_last_producer_is_consumed_as_is():
+    """SURVEY 8f rank 1 (unet_encoder.py:103-111): features in torch.channels_last memory format go to the kernel without a
+    permute copy (wsmg_dims.feat_nhwc) and give the same bits as the NCHW path; the oracle confirms the values.  Real
+    shapes (compile-time geometry build), two steps, plus the host-buffer pipeline with an NHWC pinned tensor."""
+    from wsmgmap_b200 import ops
+    c, hf, hd, n = 64, 224, 256, 3
+    gen = torch.Generator().manual_seed(12)
+    a, b = RGBMapping(_cfg(n, c)), RGBMapping(_cfg(n, c))
+    orc = OracleMapper(n, c)
+    for t in range(2):
+        feat = make_features(n, c, hf, hf, gen, signed=(t == 1))
+        depth = make_depth(("room4", "uniform")[t], n, hd, hd, gen)
+        gps, compass = torch.randn(n, 2, generator=gen), torch.rand(n, 1, generator=gen) * 6 - 3
+        masks = torch.full((n, 1), float(t))
+        obs = lambda: dict(depth=depth.to(DEV), gps=gps.to(DEV), compass=compass.to(DEV))  # noqa: E731
+        f_cl = feat.to(DEV).contiguous(memory_format=torch.channels_last)
+        assert ops.is_channels_last(f_cl) and f_cl.shape == feat.shape
+        oa = a(feat.to(DEV), obs(), masks.to(DEV))
+        ob = b(f_cl, obs(), masks.to(DEV))
+        want = orc.step(feat, depth, gps, compass, masks)
+        assert torch.equal(oa, ob) and torch.equal(a.full_global_map, b.full_global_map)
+        assert _close(ob.cpu(), want, float(want.abs().max())) and _close(b.full_global_map.cpu(), orc.full_global_map, float(want.abs().max()))
+    # host-buffer entry with an NHWC pinned tensor, dead rows skipped: the span of live rows is one contiguous copy
+    d = ops.dims_for(feat.shape, depth.shape, n, feat_nhwc=True)
+    pipe = ops.HostPipeline(d, DEV, chunk_envs=2, skip_dead_rows=True)
+    pipe.staging.fill_(0xFF)
+    g3 = torch.zeros(n, 240, 240, c, device=DEV)
+    ego_h = torch.empty(n, c, 100, 100).pin_memory()
+    f_h = feat.permute(0, 2, 3, 1).contiguous().pin_memory()             # [n,Hf,Wf,C] in memory
+    pipe.step(f_h, depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), torch.zeros(n, 1).pin_memory(), g3, ego_h)
+    g4 = torch.zeros(n, 240, 240, c, device=DEV)
+    ego4 = ops.map_update(feat.to(DEV), depth.to(DEV), gps.to(DEV), compass.to(DEV), torch.zeros(n, 1, device=DEV), g4)
+    torch.cuda.synchronize()
+    assert torch.equal(ego_h, ego4.cpu()) and torch.equal(g3, g4)
+
+
 def test_optin_extras_env_slots_and_half_store():
     """slot table instead of map[state_index]; fp16 ego map for the rollout store.  Both are
     checked against the ORACLE stepped the reference's way (re-indexed state), not only against each other."""

@@ -279,3 +279,23 @@ def test_random_small_geometries_match_spec():
 
     run()
 
+
+
+@pytest.mark.parametrize("c,e,gl,hf,hd", [(64, 100, 240, 224, 256), (8, 31, 64, 32, 40)])
+def test_channels_last_features_match_nchw(c, e, gl, hf, hd):
+    """a channels_last producer ([bs,Hf,Wf,C] in memory, wsmg_dims.feat_nhwc) gives bit-identical maps to
+    the NCHW path -- the emulated CTA body at the reference shapes and at a small run-time geometry."""
+    bs = 2
+    gen = torch.Generator().manual_seed(c + e)
+    res = 0.12 * 100 / e
+    feat = make_features(bs, c, hf, hf, gen, signed=True).numpy()
+    depth = make_depth("near", bs, hd, hd, gen)[..., 0].numpy()
+    gps = (torch.randn(bs, 2, generator=gen) * (res / 0.12)).numpy()
+    compass = (torch.rand(bs, 1, generator=gen) * 6 - 3).numpy()
+    trig = _trig(torch.from_numpy(compass))
+    masks = np.zeros((bs, 1), np.float32)
+    g0 = np.zeros((bs, gl, gl, c), np.float32)
+    g1 = np.zeros((bs, gl, gl, c), np.float32)
+    ego0, _ = emul_step(g0, feat, depth, gps, compass, masks, trig=trig, e=e, g=gl, res=res)
+    ego1, _ = emul_step(g1, feat, depth, gps, compass, masks, trig=trig, e=e, g=gl, res=res, feat_nhwc=True)
+    assert np.array_equal(ego0, ego1) and np.array_equal(g0, g1) and np.abs(ego0).sum() > 0

@@ -14,6 +14,7 @@ class WsmgDims(ctypes.Structure):
         ("bs", ctypes.c_int32), ("n_maps", ctypes.c_int32), ("C", ctypes.c_int32),
         ("Hf", ctypes.c_int32), ("Wf", ctypes.c_int32), ("Hd", ctypes.c_int32), ("Wd", ctypes.c_int32),
         ("E", ctypes.c_int32), ("G", ctypes.c_int32), ("resolution", ctypes.c_double), ("C_in", ctypes.c_int32),
+        ("feat_nhwc", ctypes.c_int32),
     ]
 
 
@@ -95,6 +96,6 @@ def check(rc: int, what: str) -> None:
         raise WsmgError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
 
 
-def make_dims(bs, n_maps, c, hf, wf, hd, wd, e, g, resolution, c_in=0) -> WsmgDims:
+def make_dims(bs, n_maps, c, hf, wf, hd, wd, e, g, resolution, c_in=0, feat_nhwc=0) -> WsmgDims:
     return WsmgDims(int(bs), int(n_maps), int(c), int(hf), int(wf), int(hd), int(wd), int(e), int(g), float(resolution),
-                    int(c_in))
+                    int(c_in), int(feat_nhwc))

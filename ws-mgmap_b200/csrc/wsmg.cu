@@ -235,13 +235,13 @@ __global__ void __launch_bounds__(CELLS_THREADS) k_cells(const float* __restrict
 }
 
 // ------------------------------------------------------------------ k_fused
-template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL>
+template <int CE, int CG, int CHW, bool VEC, bool TMA, int FEAT>
 __global__ void __launch_bounds__(FUSED_NT, 1) k_fused(const __grid_constant__ FusedParams p) {
   // One CTA per (env, slab).  (A persistent loop over the items was measured twice -- one 1024-thread CTA per SM in
   // round 1, two 512-thread CTAs per SM in round 2 -- and is not faster: the hardware already overlaps CTA launch with
   // the previous CTA's tail.)
   extern __shared__ __align__(1024) unsigned char smem[];
-  fused_body<FUSED_NT, CE, CG, CHW, VEC, TMA, POOL>(p, blockIdx.x, smem, threadIdx.x);
+  fused_body<FUSED_NT, CE, CG, CHW, VEC, TMA, FEAT>(p, blockIdx.x, smem, threadIdx.x);
 }
 
 // ------------------------------------------------------------------ k_semcrop
@@ -275,7 +275,7 @@ static const GeoPlan& geo_plan(const wsmg_dims* d) {
   static thread_local GeoPlan gp;
   static thread_local bool valid = false;
   const bool same = valid && d->C == last.C && d->Hf == last.Hf && d->Wf == last.Wf && d->Hd == last.Hd && d->Wd == last.Wd &&
-                    d->E == last.E && d->G == last.G && d->resolution == last.resolution && d->C_in == last.C_in;   // (bs, n_maps: not geometry)
+                    d->E == last.E && d->G == last.G && d->resolution == last.resolution && d->C_in == last.C_in && d->feat_nhwc == last.feat_nhwc;   // (bs, n_maps: not geometry)
   if (!same) {
     gp.g = make_geo(d);
     gp.sp = make_plan(gp.g);
@@ -399,16 +399,16 @@ static Switches switches() {
   return s;
 }
 
-template <int CE, int CG, int CHW, bool VEC, bool TMA, bool POOL = false>
+template <int CE, int CG, int CHW, bool VEC, bool TMA, int FEAT = FEAT_NCHW>
 static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s, int dev, bool pdl) {
   static int attr_set_for[64] = {0};          // dynamic shared memory opt-in, once per device and size
   if (attr_set_for[dev] < p.sp.total) {
-    cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
+    cudaError_t e = cudaFuncSetAttribute(k_fused<CE, CG, CHW, VEC, TMA, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sp.total);
     if (e != cudaSuccess) return (int)e;
     attr_set_for[dev] = p.sp.total;
   }
   if (!pdl) {
-    k_fused<CE, CG, CHW, VEC, TMA, POOL><<<grid, FUSED_NT, p.sp.total, s>>>(p);
+    k_fused<CE, CG, CHW, VEC, TMA, FEAT><<<grid, FUSED_NT, p.sp.total, s>>>(p);
     return (int)cudaGetLastError();
   }
   // Programmatic dependent launch behind k_cells: the CTAs are scheduled while k_cells' last blocks drain and run their
@@ -419,7 +419,7 @@ static int launch_fused_t(const FusedParams& p, int grid, cudaStream_t s, int de
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, k_fused<CE, CG, CHW, VEC, TMA, POOL>, p);
+  return (int)cudaLaunchKernelEx(&cfg, k_fused<CE, CG, CHW, VEC, TMA, FEAT>, p);
 }
 
 static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s, bool pdl = false) {
@@ -442,8 +442,14 @@ static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s, bool 
     if (rc != 0) return rc;
   }
   if (p.g.Cin != p.g.C) {                                   // channel pool fused in the scatter: run-time geometry builds
-    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, true>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false, true>(p, grid, s, di.dev, pdl);
-    return launch_fused_t<0, 0, 0, false, false, true>(p, grid, s, di.dev, pdl);
+    if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, FEAT_POOL>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false, FEAT_POOL>(p, grid, s, di.dev, pdl);
+    return launch_fused_t<0, 0, 0, false, false, FEAT_POOL>(p, grid, s, di.dev, pdl);
+  }
+  if (p.g.feat_nhwc) {                                      // channels_last features (validated: C % 4 == 0, no pool)
+    if (!aligned16(p.feat) && !p.stop_after_scatter && p.proj_in == nullptr) return WSMG_E_ALIGN;
+    if (tma && p.g.E == 100 && p.g.G == 240 && p.g.Hf * p.g.Wf == 224 * 224 && !sw.generic)
+      return launch_fused_t<100, 240, 224 * 224, true, true, FEAT_NHWC>(p, grid, s, di.dev, pdl);
+    return tma ? launch_fused_t<0, 0, 0, true, true, FEAT_NHWC>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false, FEAT_NHWC>(p, grid, s, di.dev, pdl);
   }
   const bool ref_geo = vec && p.g.E == 100 && p.g.G == 240 && !sw.generic;
   if (ref_geo && p.g.Hf * p.g.Wf == 224 * 224) {          // the reference's shapes (vlnce_task.yaml:11-18)
@@ -758,6 +764,11 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
         live_rows_host(g, depth_host + (size_t)(b0 + k) * de, col_src, col_xx, &lo, &hi);
         if (lo > hi) continue;                                   // nothing in this frame can write
         const size_t first = (size_t)lo * d->Wf;
+        if (d->feat_nhwc) {                                      // rows lo..hi of an NHWC frame are one contiguous span
+          const size_t off = first * planes, cnt = (size_t)(hi - lo + 1) * d->Wf * planes;
+          ck(cudaMemcpyAsync(hs.feat + (size_t)k * fe + off, feat_host + (size_t)(b0 + k) * fe + off, cnt * 4, cudaMemcpyHostToDevice, s));
+          continue;
+        }
         ck(cudaMemcpy2DAsync(hs.feat + (size_t)k * fe + first, pitch, feat_host + (size_t)(b0 + k) * fe + first, pitch,
                              (size_t)(hi - lo + 1) * d->Wf * 4, planes, cudaMemcpyHostToDevice, s));
       }

@@ -299,7 +299,9 @@ WSMG_HD int32_t rot_row_bounds(const Geo& g, float cs1, float sn1, int row) {
 // at compile time (the reference's 100 / 240 / 224*224); 0: read from p.g.
 // VEC: C % 4 == 0, so every (cell, slab) of the NHWC map is one aligned 16-byte word.
 // TMA: the map window moves through cp.async.bulk.tensor (needs VEC); else cp.async + st.global.
-// POOL: feature channels != map channels, the channel pool of rgb_mapping.py:81-84 runs inside the scatter.
+// FEAT: how the features arrive.  FEAT_NCHW: [bs,C,Hf,Wf]; FEAT_POOL: NCHW with C_in != C, the channel pool of
+// rgb_mapping.py:81-84 runs inside the scatter; FEAT_NHWC: [bs,Hf,Wf,C] (a channels_last producer) -- a
+// pixel's four slab channels are one 16-byte word, so the staging slots hold one F4 per PIXEL instead of per channel.
 // Phase-skipping switch of the profiling build (build.py --phase-skip -> lib/libwsmg_phaseskip.so): bit 1 scatter,
 // 2 first rotation, 4 band loop, 8 output rotation, 16 crop, 32 fuse, 64 TMA-arrival wait, 512 key decode,
 // 1024 translation tables, 2048 key-plane init, 4096 return at entry (launch cost of an empty CTA),
@@ -311,7 +313,9 @@ WSMG_HD int32_t rot_row_bounds(const Geo& g, float cs1, float sn1, int row) {
 #define WSMG_SKIP(bit) false
 #endif
 
-template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA_BUILD, bool POOL>
+constexpr int FEAT_NCHW = 0, FEAT_POOL = 1, FEAT_NHWC = 2;
+
+template <int NT, int CE, int CG, int CHW, bool VEC, bool TMA_BUILD, int FEAT>
 WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, const int tid) {
   const Geo& g = p.g;
   const SmemPlan& sp = p.sp;
@@ -486,7 +490,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     // Channel pool (rgb_mapping.py:81-84) fused: when Cin != C the scatter runs once per input plane of a bin,
     // all passes reducing into the same key plane (max over channels commutes with the max-scatter).
     const int Cin = g.Cin;
-    constexpr bool pool = POOL;
+    constexpr bool pool = FEAT == FEAT_POOL;
+    constexpr bool nhwc = FEAT == FEAT_NHWC;
+    static_assert(!nhwc || VEC, "NHWC features need C % 4 == 0");
     int bin_lo[SLAB], bin_n[SLAB], passes = 1;
 #pragma unroll
     for (int ch = 0; ch < SLAB; ++ch) {
@@ -495,7 +501,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       bin_n[ch] = pool ? pool_end(k, Cin, C) - bin_lo[ch] : 1;
       passes = bin_n[ch] > passes ? bin_n[ch] : passes;
     }
-    const float* feat_b = p.feat + (size_t)b * Cin * HW;
+    const float* feat_b = p.feat + (size_t)b * Cin * HW;     // (the same element count per env in either layout)
     const int n4 = HW / 4;
     for (int pass = 0; pass < passes; ++pass) {
     size_t plane_off[SLAB];                                   // element offset of this pass's input plane per output channel
@@ -522,11 +528,18 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const float* feat_slab = feat_b + (size_t)c0 * HW;        // plane of the slab's first channel (no pool)
     auto issue = [&](int slot, int tt, uint2 c) {
       if (is_live(c)) {
-        const float* src = (pool ? feat_b : feat_slab) + 4 * (size_t)tt;
         F4* dst = stage + slot * SLAB * NT + tid;
+        if (nhwc) {                           // pixel 4*tt + px, channels c0..c0+3: one aligned 16-byte word each
+          const float* src = feat_b + 4 * (size_t)tt * Cin + c0;
 #pragma unroll
-        for (int ch = 0; ch < SLAB; ++ch)   // without the pool the four planes are compile-time offsets of one pointer
-          if (ch < nch && !WSMG_SKIP(32768)) async_copy16(dst + ch * NT, src + (pool ? plane_off[ch] : (size_t)ch * HW), true);
+          for (int px = 0; px < 4; ++px)
+            if (!WSMG_SKIP(32768)) async_copy16(dst + px * NT, src + (size_t)px * Cin, true);
+        } else {
+          const float* src = (pool ? feat_b : feat_slab) + 4 * (size_t)tt;
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch)   // without the pool the four planes are compile-time offsets of one pointer
+            if (ch < nch && !WSMG_SKIP(32768)) async_copy16(dst + ch * NT, src + (pool ? plane_off[ch] : (size_t)ch * HW), true);
+        }
       }
       async_commit();                                          // one group per step, live or not: wait counts stay exact
     };
@@ -553,6 +566,15 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         F4 f[SLAB];
 #pragma unroll
         for (int ch = 0; ch < SLAB; ++ch) f[ch] = ch < nch ? stage[(slot * SLAB + ch) * NT + tid] : f4_zero();
+        if (nhwc) {                           // slots hold pixels: transpose to f[channel].v[pixel] (register renaming)
+          F4 gq[4];
+#pragma unroll
+          for (int px = 0; px < 4; ++px) gq[px] = f[px];
+#pragma unroll
+          for (int ch = 0; ch < SLAB; ++ch)
+#pragma unroll
+            for (int px = 0; px < 4; ++px) f[ch].v[px] = gq[px].v[ch];
+        }
         // Runs of equal codes are reduced in registers with a predicated running max (the sign of a zero is
         // irrelevant, finish_cell() turns -0 into +0 like the reference): one shared-memory reduction per run and
         // channel.  A pixel that does not write never flushes, and the run restarts whenever the code changes,

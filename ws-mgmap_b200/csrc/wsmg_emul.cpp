@@ -92,11 +92,12 @@ int wsmg_emul_step(const float* feat, const float* depth, const float* gps, cons
   for (int blk = 0; blk < d->bs * slabs; ++blk) {
     memset(sm, 0xCD, sp.total);     // poison: nothing may rely on zeroed shared memory
     const bool pool = g.Cin != g.C;
-    if (pool && g.C % 4 == 0) fused_body<1, 0, 0, 0, true, false, true>(p, blk, sm, 0);
-    else if (pool) fused_body<1, 0, 0, 0, false, false, true>(p, blk, sm, 0);
-    else if (g.C % 4 == 0 && g.E == 100 && g.G == 240 && HW == 224 * 224 && !generic) fused_body<1, 100, 240, 224 * 224, true, false, false>(p, blk, sm, 0);
-    else if (g.C % 4 == 0) fused_body<1, 0, 0, 0, true, false, false>(p, blk, sm, 0);
-    else fused_body<1, 0, 0, 0, false, false, false>(p, blk, sm, 0);
+    if (pool && g.C % 4 == 0) fused_body<1, 0, 0, 0, true, false, FEAT_POOL>(p, blk, sm, 0);
+    else if (pool) fused_body<1, 0, 0, 0, false, false, FEAT_POOL>(p, blk, sm, 0);
+    else if (g.feat_nhwc) fused_body<1, 0, 0, 0, true, false, FEAT_NHWC>(p, blk, sm, 0);
+    else if (g.C % 4 == 0 && g.E == 100 && g.G == 240 && HW == 224 * 224 && !generic) fused_body<1, 100, 240, 224 * 224, true, false, FEAT_NCHW>(p, blk, sm, 0);
+    else if (g.C % 4 == 0) fused_body<1, 0, 0, 0, true, false, FEAT_NCHW>(p, blk, sm, 0);
+    else fused_body<1, 0, 0, 0, false, false, FEAT_NCHW>(p, blk, sm, 0);
   }
   return 0;
 }

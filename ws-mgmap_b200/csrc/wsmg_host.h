@@ -18,6 +18,7 @@ inline int validate_dims(const wsmg_dims* d) {
   if (d->E > d->G) return WSMG_E_EGO_GT_GLOBAL;
   if (d->n_maps < d->bs) return WSMG_E_BATCH;
   if (d->C_in < 0) return WSMG_E_CHANNELS;
+  if (d->feat_nhwc != 0 && (d->feat_nhwc != 1 || d->C % 4 != 0 || (d->C_in != 0 && d->C_in != d->C))) return WSMG_E_CHANNELS;
   if ((d->Hf * d->Wf) % 4 != 0) return WSMG_E_ALIGN;
   if ((long long)d->Hf * d->Wf > 63LL * 2048) return WSMG_E_DIMS;   // per-block flag words of the k_cells launch (wsmg_host.h MAX_FLAG_WORDS)
   if (d->E > 126 || d->G > 32768) return WSMG_E_DIMS;          // 16-bit fan codes; (E+2)/8 bands must fit the barrier array; row tables of 128
@@ -27,6 +28,7 @@ inline int validate_dims(const wsmg_dims* d) {
 inline Geo make_geo(const wsmg_dims* d) {
   Geo g;
   g.Cin = d->C_in > 0 ? d->C_in : d->C;
+  g.feat_nhwc = d->feat_nhwc;
   g.E = d->E; g.G = d->G; g.C = d->C; g.Hf = d->Hf; g.Wf = d->Wf; g.Hd = d->Hd; g.Wd = d->Wd;
   const double cmin = -(double)d->G * d->resolution / 2;       // rgb_mapping.py:21
   const double cmax = (double)d->G * d->resolution / 2;        // rgb_mapping.py:22

@@ -25,6 +25,7 @@ constexpr float SENTINEL = -1e16f;           // rgb_mapping.py:187
 struct Geo {
   int E, G, C, Hf, Wf, Hd, Wd;
   int Cin;               // channels of the feature tensor (== C unless the channel pool of rgb_mapping.py:81-84 applies)
+  int feat_nhwc;         // features are [bs,Hf,Wf,C] in memory (channels_last producer) instead of [bs,C,Hf,Wf]
   int paste_lo;          // G/2 - floor(E/2)                      rgb_mapping.py:42
   int fan_rows;          // rows of the ego grid a depth >= 0 pixel can reach
   int fan_cells;         // packed cells of the fan

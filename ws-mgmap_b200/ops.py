@@ -18,7 +18,7 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _chk(t, name, device=None, dtype=torch.float32, numel=None, optional=False):
+def _chk(t, name, device=None, dtype=torch.float32, numel=None, optional=False, channels_last_ok=False):
     """The C ABI reads raw pointers: refuse anything it would misread."""
     if t is None:
         if optional:
@@ -30,17 +30,24 @@ def _chk(t, name, device=None, dtype=torch.float32, numel=None, optional=False):
         raise ValueError(f"{name} is on {t.device}, expected {device}")
     if t.dtype != dtype:
         raise ValueError(f"{name} has dtype {t.dtype}, expected {dtype}")
-    if not t.is_contiguous():
+    if not (t.is_contiguous() or (channels_last_ok and is_channels_last(t))):
         raise ValueError(f"{name} must be contiguous")
     if numel is not None and t.numel() != numel:
         raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
 
 
-def dims_for(feat_shape, depth_shape, n_maps, e=100, g=240, resolution=0.12, map_depth=None):
-    """map_depth: channels of the map when they differ from the features' (channel pool fused in the kernel)."""
+def dims_for(feat_shape, depth_shape, n_maps, e=100, g=240, resolution=0.12, map_depth=None, feat_nhwc=False):
+    """map_depth: channels of the map when they differ from the features' (channel pool fused in the kernel);
+    feat_nhwc: the feature tensor is channels_last in memory ([bs,Hf,Wf,C]); feat_shape stays the logical NCHW shape."""
     bs, c_in, hf, wf = feat_shape
     c = c_in if map_depth is None else map_depth
-    return _lib.make_dims(bs, n_maps, c, hf, wf, depth_shape[1], depth_shape[2], e, g, resolution, c_in=0 if c == c_in else c_in)
+    return _lib.make_dims(bs, n_maps, c, hf, wf, depth_shape[1], depth_shape[2], e, g, resolution, c_in=0 if c == c_in else c_in,
+                          feat_nhwc=1 if feat_nhwc else 0)
+
+
+def is_channels_last(t) -> bool:
+    """A 4-D tensor whose memory is [N,H,W,C] (torch.channels_last) and not also plain contiguous."""
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
 
 
 def scratch_bytes(dims) -> int:
@@ -67,13 +74,14 @@ def map_update(feat, depth, gps, compass, mask, gmap, e=100, resolution=0.12, tr
     dev = gmap.device
     bs = feat.shape[0]
     _chk(gmap, "gmap", dev)
-    _chk(feat, "feat", dev)
+    _chk(feat, "feat", dev, channels_last_ok=True)          # a channels_last producer is consumed as it is (wsmg_dims.feat_nhwc)
     _chk(depth, "depth", dev, numel=bs * depth.shape[1] * depth.shape[2])
     _chk(gps, "gps", dev, numel=2 * bs)
     _chk(compass, "compass", dev, numel=bs)
     _chk(mask, "mask", dev, numel=bs)
     _chk(trig, "trig", dev, numel=4 * bs, optional=True)
-    d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution, map_depth=gmap.shape[3])
+    d = dims_for(feat.shape, depth.shape, gmap.shape[0], e, gmap.shape[1], resolution, map_depth=gmap.shape[3],
+                 feat_nhwc=is_channels_last(feat))
     if scratch is None:
         scratch = alloc_scratch(d, dev)
     _chk(scratch, "scratch", dev, dtype=torch.uint8)

@@ -140,10 +140,10 @@ class Mapping(nn.Module):
         self._env_slots = torch.tensor(host, dtype=torch.int32, device=self._full_global_map.device)
 
     # -- helpers ---------------------------------------------------------------------------
-    def _dims(self, bs, n_maps, hf, wf, hd, wd, c_in):
+    def _dims(self, bs, n_maps, hf, wf, hd, wd, c_in, feat_nhwc=False):
         c = self.global_map_depth
         return _lib.make_dims(bs, n_maps, c, hf, wf, hd, wd, self.egocentric_map_size, self.global_map_size,
-                              self.resolution, c_in=0 if c_in == c else c_in)
+                              self.resolution, c_in=0 if c_in == c else c_in, feat_nhwc=1 if feat_nhwc else 0)
 
     def _scratch_for(self, dims, device):
         need = self._lib.wsmg_scratch_bytes(ctypes.byref(dims))
@@ -175,7 +175,15 @@ class Mapping(nn.Module):
         g, c, e = self.global_map_size, self.global_map_depth, self.egocentric_map_size
         if tuple(full_global_map.shape[1:]) != (g, g, c):
             raise ValueError(f"full_global_map has shape {tuple(full_global_map.shape)}, expected [n,{g},{g},{c}]")
-        features = self._f32c(features, "features", dev)
+        # A channels_last feature tensor (what cuDNN's NHWC convolutions hand over when the UNet runs in that memory
+        # format, unet_encoder.py:103-111) is consumed as it is: no permute copy.  Anything else is made NCHW-contiguous.
+        nhwc = (isinstance(features, torch.Tensor) and features.dtype == torch.float32 and ops.is_channels_last(features)
+                and features.shape[1] == c and c % 4 == 0)
+        if nhwc:
+            if features.device != dev:
+                raise ValueError(f"features is on {features.device}, the map lives on {dev}")
+        else:
+            features = self._f32c(features, "features", dev)
         bs, cf, hf, wf = features.shape          # cf != c: the channel pool of rgb_mapping.py:81-84 runs inside the kernel
         if bs > full_global_map.shape[0]:
             raise ValueError(f"batch {bs} larger than the map state ({full_global_map.shape[0]} envs)")
@@ -187,7 +195,7 @@ class Mapping(nn.Module):
         masks = self._f32c(masks, "masks", dev)
         if gps.shape != (bs, 2) or compass.numel() != bs or masks.numel() != bs:
             raise ValueError("gps must be [bs,2], compass [bs,1], masks [bs,1]")
-        dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2], cf)
+        dims = self._dims(bs, full_global_map.shape[0], hf, wf, depth.shape[1], depth.shape[2], cf, nhwc)
         scratch = self._scratch_for(dims, dev)
         slots = self._env_slots
         if slots is not None:
