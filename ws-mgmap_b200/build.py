@@ -54,17 +54,20 @@ def _sources():
     return out
 
 
-def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = False) -> str:
+def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = False, variant: str = "", defines=()) -> str:
     """phase_skip=True builds the profiling variant lib/libwsmg_phaseskip.so (-DWSMG_PHASE_SKIP, see
-    csrc/wsmg_body.h: WSMG_SKIP); load it with WSMG_LIB_PATH, never in production."""
+    csrc/wsmg_body.h: WSMG_SKIP); load it with WSMG_LIB_PATH, never in production.  `variant` + `defines` build an
+    experiment library lib/libwsmg_<variant>.so with extra -D switches (scripts/variants.py)."""
     os.makedirs(LIB, exist_ok=True)
-    target = os.path.join(LIB, "libwsmg_phaseskip.so" if phase_skip else "libwsmg.so")
+    target = os.path.join(LIB, f"libwsmg_{variant}.so" if variant else ("libwsmg_phaseskip.so" if phase_skip else "libwsmg.so"))
     if not force and _newer(target, _sources()):
         return target
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", target, os.path.join(CSRC, "wsmg.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    for d in defines:
+        cmd.insert(1, "-D" + d)
     if phase_skip:
         cmd.insert(1, "-DWSMG_PHASE_SKIP")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -193,6 +193,7 @@ __device__ __forceinline__ void tma_load_box(void* dst, const void* tmap, int c,
                ::"r"(saddr(dst)), "l"(tmap), "r"(c), "r"(v), "r"(u), "r"(b), "r"(saddr(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int id, int threads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory"); }
 #else
 inline void smem_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
 inline bool warp_all_nonneg(int32_t bits) { return bits >= 0; }
@@ -216,6 +217,7 @@ inline void mbar_expect_tx(uint64_t*, unsigned) {}
 inline void mbar_wait(uint64_t*, unsigned) {}
 inline void tma_load_box(void*, const void*, int, int, int, int, uint64_t*) {}
 inline void fence_proxy_async() {}
+inline void group_sync(int, int) {}
 #endif
 
 // Tap that skips the shared-memory read when the index says "zero cell" (out of range, or a tap whose
@@ -418,10 +420,14 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // TMA: boxes of TMA_ROWS x WWP cells, issued by the first lanes of the last warp (it owns no window / crop
   // cell).  Columns beyond the window and rows beyond its last one are loaded (or zero-filled outside the
   // tensor) and never read.
-  const int tma_lane = tid - (NT - 32);                     // 0..31 in the TMA warp, negative elsewhere
+  // The band loop (phase 3) gives every thread at most one window cell and one crop cell per trip: BAND * (E + 2) cells.
+  // Only the warps that own one run it, paced by a named barrier of their own -- the rest would just lengthen every
+  // trip's barrier (measured: 3.505 -> 3.452 ms per 1024-env step with 26 instead of 32 warps at E = 100).
+  const int LT = NT >= 64 ? (((BAND * WW + 31) / 32 * 32) < NT ? ((BAND * WW + 31) / 32 * 32) : NT) : NT;   // loop threads
+  const int tma_lane = tid - (LT - 32);                     // 0..31 in the TMA warp (the last loop warp), else outside [0, 32)
   auto prefetch_band = [&](int k) {
     if (TMA) {
-      if (tma_lane >= 0) {
+      if ((unsigned)tma_lane < 32u) {
         const int left = WW - k * BAND;
         const int boxes = left >= BAND ? BAND / TMA_ROWS : (left + TMA_ROWS - 1) / TMA_ROWS;
         if (tma_lane == 0) mbar_expect_tx(&bars[k], (unsigned)(boxes * TMA_ROWS * WWP * 16));
@@ -453,7 +459,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
   };
   if (!p.stop_after_scatter) {
-    if (TMA && tma_lane >= 0) {
+    if (TMA && (unsigned)tma_lane < 32u) {
       if (tma_lane == 0) {
         for (int k = 0; k < NB; ++k) mbar_init(&bars[k], 1);
         mbar_init_fence();
@@ -789,7 +795,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   // X row p, which only F rows p..p+2 read -- so rows p <= done-3 are safe.  One barrier per trip.
   int p_lo = 0;
   auto fuse_band = [&](int k) {                              // 3a: F rows of band k, in place in the ring
-    for (int t = tid; t < BAND * WW; t += NT) {
+    for (int t = tid; t < BAND * WW; t += LT) {
       int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
       if (uu >= WW) continue;
       const I4 ct = colT[vv], rt = rowT[uu];
@@ -828,7 +834,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   auto crop_rows = [&](int k) {                              // 3b: B rows whose F rows were finished before trip k
     int done = k * BAND < WW ? k * BAND : WW;
     int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
-    for (int t = tid; t < (p_hi - p_lo) * E; t += NT) {
+    for (int t = tid; t < (p_hi - p_lo) * E; t += LT) {
       int dr = t / E, q = t - dr * E, pr = p_lo + dr;
       const I4 bx = bXT[q], by = bYT[pr];
       Weights w = make_weights(as_float(bx.c), as_float(by.c));
@@ -837,15 +843,18 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     }
     p_lo = p_hi;
   };
+  if (TMA && tid >= LT) {
+    // no cell of the loop is ours: meet the others at the barrier behind it
+  } else
   for (int k = 0; k <= (WSMG_SKIP(4) ? -1 : NB); ++k) {
     if (!TMA && k < NB) {
       if (k + 1 < NB) async_wait<1>(); else async_wait<0>();
     }
-    WSMG_SYNC();
+    if (TMA) group_sync(1, LT); else WSMG_SYNC();           // (the cp.async build prefetches with every thread)
     if (TMA) {
       // ring rows of band k+2 were last read by trip k-1's crop (RR >= 4*BAND + 2) and last written by an
       // earlier fuse (fenced below): the barrier above makes them free for the TMA unit to overwrite
-      if (tma_lane >= 0 && k + 2 < NB) prefetch_band(k + 2);
+      if ((unsigned)tma_lane < 32u && k + 2 < NB) prefetch_band(k + 2);
       if (k >= 1 && !WSMG_SKIP(16)) crop_rows(k);    // needs only finished F rows: runs while band k is still landing
       if (k < NB) {
         if (!WSMG_SKIP(64)) mbar_wait(&bars[k], 0);
