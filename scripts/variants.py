@@ -29,7 +29,7 @@ def child(envs):
     cg = torch.Generator().manual_seed(1)
     kinds = [make_depth(k, 8, 256, 256, cg) for k in ("uniform", "near", "room2", "room4")]
     depth = torch.stack([kinds[b % 4][(b // 4) % 8] for b in range(n)], 0).to(dev).contiguous()
-    gps = torch.randn(n, 2, device=dev); compass = torch.rand(n, 1, device=dev) * 6 - 3
+    gps = torch.randn(n, 2, device=dev, generator=gen); compass = torch.rand(n, 1, device=dev, generator=gen) * 6 - 3
     ones = torch.ones(n, 1, device=dev)
     gmap = torch.zeros(n, 240, 240, c, device=dev)
     d = ops.dims_for(feat.shape, depth.shape, n)
