@@ -66,8 +66,9 @@ class WsmgError(RuntimeError):
 
 def load() -> ctypes.CDLL:
     """Load libwsmg.so.  Where nvcc exists (the build container) the library is first rebuilt in-tree if it is
-    missing or older than its sources (build.build_cuda compares mtimes, a no-op otherwise); on a box without
-    nvcc the shipped .so is used as it is, and a missing one raises -- there is no fallback."""
+    missing or was built from other sources (build.build_cuda compares a content hash of csrc/ + include/ with the
+    stamp next to the .so; a no-op when they agree); on a box without nvcc the shipped .so is used as it is, and a
+    missing one raises -- there is no fallback."""
     global _lib
     if _lib is not None:
         return _lib
