@@ -329,21 +329,23 @@ def time_resident(res, K, W, barrier, flush_buf=None):
     return elapsed_ms, fused_ms, checksum
 
 
-def pcie_ceiling(dev, barrier, mb=256, reps=6):
-    """Pinned-memory cudaMemcpyAsync bandwidth of this rank's link with both directions busy at once (all ranks run
-    it together): the ceiling of any end-to-end number.  Returns (H2D GB/s, D2H GB/s)."""
+def pcie_ceiling(dev, barrier, h2d_bytes, d2h_bytes, reps=6):
+    """What the host links allow for ONE e2e step of this rank: pinned cudaMemcpyAsync of exactly the step's byte mix
+    (`h2d_bytes` in, `d2h_bytes` out, on two streams at once), all ranks running it together -- so that whatever the
+    ranks share (root complex, host memory) is shared here as well.  Returns (ms per step, H2D GB/s, D2H GB/s)."""
     import torch
-    n = mb << 20
-    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
-    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    h2d_bytes, d2h_bytes = max(int(h2d_bytes), 1 << 20), max(int(d2h_bytes), 1 << 20)
+    h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     for _ in range(2):
         with torch.cuda.stream(s1):
             d_in.copy_(h_in, non_blocking=True)
         with torch.cuda.stream(s2):
             h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize(dev)
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -357,7 +359,8 @@ def pcie_ceiling(dev, barrier, mb=256, reps=6):
     a1.record(s1)
     b1.record(s2)
     barrier()
-    return reps * n / (a0.elapsed_time(a1) * 1e6), reps * n / (b0.elapsed_time(b1) * 1e6)
+    ta, tb = a0.elapsed_time(a1), b0.elapsed_time(b1)
+    return max(ta, tb) / reps, reps * h2d_bytes / (ta * 1e6), reps * d2h_bytes / (tb * 1e6)
 
 
 def run_e2e(args, n, dev, rank, barrier):
@@ -516,7 +519,7 @@ def run_native(args, rank, local_rank, world):
 
     # ---- end to end from pinned host buffers (`e2e`) and the link's ceiling measured in the same run --------
     e2e = run_e2e(args, n, dev, rank, barrier)
-    h2d_gbs, d2h_gbs = pcie_ceiling(dev, barrier)
+    link_ms, h2d_gbs, d2h_gbs = pcie_ceiling(dev, barrier, e2e["h2d"], e2e["d2h"])
 
     # ---- comparators on one GPU: the reference's ops on this GPU, index flips against them, the policy forward ----
     torch_cuda, flips, policy_rec = None, None, None
@@ -556,7 +559,7 @@ def run_native(args, rank, local_rank, world):
 
     # ---- gather (max over ranks) ---------------------------------------------------------------------------
     stats = torch.tensor([elapsed_ms, fused_ms, e2e["ms"], checksum, float(n), weak_ms or 0.0, h2d_gbs, d2h_gbs,
-                          float(e2e["h2d"]), float(e2e["d2h"]), float(e2e["dense"])], dtype=torch.float64, device=dev)
+                          float(e2e["h2d"]), float(e2e["d2h"]), float(e2e["dense"]), link_ms], dtype=torch.float64, device=dev)
     allst = shard.gather_stats(stats)             # the only collective: a few dozen bytes over NVLink
     if rank == 0:
         max_ms = float(allst[:, 0].max())
@@ -574,7 +577,7 @@ def run_native(args, rank, local_rank, world):
         e2e_fps = ne * world * Ke / (max_e2e / 1e3)
         h2d_step, d2h_step = float(allst[:, 8].sum()), float(allst[:, 9].sum())
         link_h2d, link_d2h = float(allst[:, 6].min()), float(allst[:, 7].min())
-        ceiling = min(link_h2d * 1e9 / (h2d_step / (ne * world)), link_d2h * 1e9 / (d2h_step / (ne * world))) * world
+        ceiling = ne * world / (float(allst[:, 11].max()) / 1e3)      # frames/s if a step were nothing but its copies
         line = {
             "metric": "map-update frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": cfg["scaling"],
@@ -591,9 +594,10 @@ def run_native(args, rank, local_rank, world):
                     "mode": args.e2e_mode, "numa_node_rank0": numa_node, "numa_note": numa_note,
                     "h2d_bytes_per_step_dense": float(allst[:, 10].sum()),
                     "pcie_ceiling_gbs": {"h2d": link_h2d, "d2h": link_d2h,
-                                         "how": "pinned cudaMemcpyAsync, both directions at once, all ranks together, min over ranks"},
+                                         "how": "pinned cudaMemcpyAsync of one e2e step's byte mix (h2d_bytes_per_step in, d2h_bytes_per_step "
+                                                "out, two streams at once), all ranks together; GB/s = min over ranks, ceiling = envs / slowest rank's time"},
                     "pcie_ceiling_frames_per_s": ceiling, "frac_of_pcie_ceiling": e2e_fps / ceiling},
-            "gpu_launches": 3 * K * world,
+            "gpu_launches": 2 * K * world,               # k_cells (+ reset / rotation-setup blocks) and k_fused per step and rank
             "clocks": clk.summary(),
             "checksums": [float(x) for x in allst[:, 3]],
             "by_depth": by_depth,
