@@ -40,6 +40,7 @@ with open(f"profiles/{tag}_k_fused_ncu_full.txt", "w") as f:
 PY
 ncu -i gpurun_out/prof_fused.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null > /tmp/src_$TAG.csv
 { echo "# executed-instruction / stall-sample breakdown of k_fused by SASS segment (scripts/ncu_segments.py)"; python scripts/ncu_segments.py /tmp/src_$TAG.csv 4096 0.012;
+  echo; echo "# per phase (ranges of SASS between CTA-wide barriers, scripts/ncu_barrier_ranges.py)"; python scripts/ncu_barrier_ranges.py /tmp/src_$TAG.csv 4096;
   echo; echo "# LSU pipe: shared-memory wavefronts and global tag requests per instruction (scripts/ncu_wavefronts.py)"; python scripts/ncu_wavefronts.py /tmp/src_$TAG.csv 4096 24; } > $OUT/${TAG}_k_fused_source_breakdown.txt
 { echo "# ncu --metrics gpu__time_duration.sum --clock-control none (bench.py --envs 256 --steps 4 --warmup 3): per-launch device time, ns"; grep -E "k_fused|k_cells|k_reset" gpurun_out/launches.csv | awk -F'","' '{print $5, $(NF)}' | tr -d '"' | tail -24; } > $OUT/${TAG}_launches.txt
 cp gpurun_out/bench.json $OUT/${TAG}_bench_sweep1024.json 2>/dev/null
