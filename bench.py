@@ -636,7 +636,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="strong (default for sweep1024): the env count in total, sharded; weak: that many per GPU")
     ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU in the host-buffer (e2e) leg")
-    ap.add_argument("--e2e-chunk", type=int, default=16)
+    ap.add_argument("--e2e-chunk", type=int, default=4, help="largest chunk of the host-buffer entry (it ramps up to and down from this size)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-mode", default="rows", choices=["copy", "rows", "zerocopy"],
                     help="host-buffer leg: stage the whole feature tensor, only the rows that hold a writing pixel, "

@@ -746,9 +746,15 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
   ck(cudaStreamWaitEvent(st[1], lanes->fork, 0));
   const size_t one = slot_bytes(d, chunk, nullptr, nullptr);
   const size_t per_map = (size_t)d->G * d->G * d->C;
-  int slot = 0;
-  for (int b0 = 0; b0 < d->bs && rc == 0; b0 += chunk, slot ^= 1) {
-    const int n = (d->bs - b0) < chunk ? (d->bs - b0) : chunk;
+  // Chunk sizes ramp up from 2 envs to `chunk` and down again at the end: the first copy is short, so the kernels start
+  // early, and so is the last one, so little is left to drain when the copy engine runs dry (measured, 128 envs, PCIe
+  // Gen5: 5.38 k frames/s with uniform chunks of 16, 5.66 k with chunks of 2 -- the ramp gets the latter without its
+  // sixty-four launches).
+  int slot = 0, n = 0, ramp = chunk < 2 ? chunk : 2;
+  for (int b0 = 0; b0 < d->bs && rc == 0; b0 += n, slot ^= 1, ramp = ramp * 2 < chunk ? ramp * 2 : chunk) {
+    const int left = d->bs - b0;
+    n = left <= 2 ? left : (ramp < (left + 1) / 2 ? ramp : (left + 1) / 2);
+    if (n > chunk) n = chunk;
     HostSlot hs;
     slot_bytes(d, chunk, &hs, (unsigned char*)staging + slot * one);
     cudaStream_t s = st[slot];

@@ -204,7 +204,7 @@ class HostPipeline:
     chunked so copies overlap the kernels (wsmg_map_update_host_ex).  zero_copy=True: the feature tensor must be
     pinned (`pin_memory()`); the scatter pulls it over the bus itself and skips the pixel groups that cannot write."""
 
-    def __init__(self, dims, device, chunk_envs=32, zero_copy=False, skip_dead_rows=False):
+    def __init__(self, dims, device, chunk_envs=4, zero_copy=False, skip_dead_rows=False):
         # skip_dead_rows: the host tests the depth frame first and copies only the feature rows that hold a pixel
         # which can write (indoor frames: about half)
         self.flags = (_lib.HOST_ZEROCOPY_FEATURES if zero_copy else 0) | (_lib.HOST_SKIP_DEAD_ROWS if skip_dead_rows else 0)
