@@ -69,8 +69,9 @@ const char* wsmg_error_string(int code);
  * Negative arguments return to the default: the environment variables WSMG_FORCE_GENERIC / WSMG_NO_TMA, read once. */
 void wsmg_debug_switches(int force_generic, int no_tma);
 
-/* Bytes of device scratch wsmg_map_update needs for `d`: packed cell codes, per-env flags and rotation tables, and one
- * crop slot (E*E*16 bytes) per resident k_fused CTA -- at most 320 slots (51 MB at E = 100), independent of bs beyond that. */
+/* Bytes of device scratch wsmg_map_update needs for `d` (0.10 MB per env at the reference shapes): packed cell codes
+ * (uint16 per sampled pixel), per-env and per-block flag words, the first rotation's column bounds and both rotations'
+ * cos / sin per env.  Contents need no initialisation and carry nothing from one call to the next. */
 size_t wsmg_scratch_bytes(const wsmg_dims* d);
 
 /* Per-env status words the update leaves in scratch (uint32 each, at byte offset wsmg_scratch_flags_offset(d)):
@@ -97,6 +98,13 @@ size_t wsmg_scratch_flags_offset(const wsmg_dims* d);
  *   ego_out  [bs,C,E,E] fp32 NCHW            (final_retrieval, :70)
  *   trig     optional [bs,4] = cos(-compass), sin(-compass), cos(compass), sin(compass) computed by
  *            the caller (parity tests pass the CPU reference's values); NULL = sinf/cosf on device.
+ * Preconditions under which the result equals the reference's (all hold for the reference's own data flow):
+ *   - gmap >= 0 everywhere (it starts at zero and only ever takes maxima of post-ReLU features or zeros): the update
+ *     reads and writes only the (E+2)^2 window the ego patch can reach, whereas rgb_mapping.py:55-56 takes
+ *     max(map, translated) over the whole G x G map, which would clamp a negative entry anywhere to 0;
+ *   - features, map, gps and compass finite (torch.max propagates NaN; fmaxf does not), depth >= 0 (see
+ *     WSMG_FLAG_OUTSIDE_FAN above);
+ *   - mask in {0, 1} as the trainers produce it (other values scale the map as the reference does, :35).
  */
 int wsmg_map_update(const float* feat, const float* depth, const float* gps, const float* compass,
                     const float* mask, float* gmap, float* ego_out, const float* trig,
