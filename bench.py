@@ -330,9 +330,13 @@ def time_resident(res, K, W, barrier, flush_buf=None):
 
 
 def pcie_ceiling(dev, barrier, h2d_bytes, d2h_bytes, reps=6):
-    """What the host links allow for ONE e2e step of this rank: pinned cudaMemcpyAsync of exactly the step's byte mix
-    (`h2d_bytes` in, `d2h_bytes` out, on two streams at once), all ranks running it together -- so that whatever the
-    ranks share (root complex, host memory) is shared here as well.  Returns (ms per step, H2D GB/s, D2H GB/s)."""
+    """What the host links allow for ONE e2e step of this rank, all ranks measuring together (whatever they share -- root
+    complex, host memory -- is shared here as well), pinned cudaMemcpyAsync only:
+      * `bound_ms`: the step's H2D bytes alone, nothing going the other way.  No pipeline can beat it: a true ceiling.
+      * `mix_ms`:   the step's H2D and D2H bytes on two streams at once, until both are through: what a perfectly
+                    overlapped pipeline with this byte mix would take if both copies started together (an estimate --
+                    at N = 8 the real pipeline, whose D2H trails its H2D, has been measured slightly faster).
+    Returns (bound_ms, mix_ms, H2D GB/s alone, H2D GB/s in the mix, D2H GB/s in the mix)."""
     import torch
     h2d_bytes, d2h_bytes = max(int(h2d_bytes), 1 << 20), max(int(d2h_bytes), 1 << 20)
     h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
@@ -340,27 +344,36 @@ def pcie_ceiling(dev, barrier, h2d_bytes, d2h_bytes, reps=6):
     d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
     d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    for _ in range(2):
-        with torch.cuda.stream(s1):
-            d_in.copy_(h_in, non_blocking=True)
-        with torch.cuda.stream(s2):
-            h_out.copy_(d_out, non_blocking=True)
-    torch.cuda.synchronize(dev)
-    barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record(s1)
-    b0.record(s2)
-    for _ in range(reps):
-        with torch.cuda.stream(s1):
-            d_in.copy_(h_in, non_blocking=True)
-        with torch.cuda.stream(s2):
-            h_out.copy_(d_out, non_blocking=True)
-    a1.record(s1)
-    b1.record(s2)
-    barrier()
-    ta, tb = a0.elapsed_time(a1), b0.elapsed_time(b1)
-    return max(ta, tb) / reps, reps * h2d_bytes / (ta * 1e6), reps * d2h_bytes / (tb * 1e6)
+
+    def run(both):
+        for _ in range(2):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            if both:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(s1)
+        b0.record(s2)
+        for _ in range(reps):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            if both:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        a1.record(s1)
+        b1.record(s2)
+        torch.cuda.synchronize(dev)
+        barrier()
+        return a0.elapsed_time(a1), b0.elapsed_time(b1)
+
+    ta_only, _ = run(False)
+    ta, tb = run(True)
+    return (ta_only / reps, max(ta, tb) / reps, reps * h2d_bytes / (ta_only * 1e6), reps * h2d_bytes / (ta * 1e6),
+            reps * d2h_bytes / (tb * 1e6))
 
 
 def run_e2e(args, n, dev, rank, barrier):
@@ -519,7 +532,7 @@ def run_native(args, rank, local_rank, world):
 
     # ---- end to end from pinned host buffers (`e2e`) and the link's ceiling measured in the same run --------
     e2e = run_e2e(args, n, dev, rank, barrier)
-    link_ms, h2d_gbs, d2h_gbs = pcie_ceiling(dev, barrier, e2e["h2d"], e2e["d2h"])
+    link_ms, mix_ms, h2d_alone_gbs, h2d_gbs, d2h_gbs = pcie_ceiling(dev, barrier, e2e["h2d"], e2e["d2h"])
 
     # ---- comparators on one GPU: the reference's ops on this GPU, index flips against them, the policy forward ----
     torch_cuda, flips, policy_rec = None, None, None
@@ -559,7 +572,7 @@ def run_native(args, rank, local_rank, world):
 
     # ---- gather (max over ranks) ---------------------------------------------------------------------------
     stats = torch.tensor([elapsed_ms, fused_ms, e2e["ms"], checksum, float(n), weak_ms or 0.0, h2d_gbs, d2h_gbs,
-                          float(e2e["h2d"]), float(e2e["d2h"]), float(e2e["dense"]), link_ms], dtype=torch.float64, device=dev)
+                          float(e2e["h2d"]), float(e2e["d2h"]), float(e2e["dense"]), link_ms, mix_ms, h2d_alone_gbs], dtype=torch.float64, device=dev)
     allst = shard.gather_stats(stats)             # the only collective: a few dozen bytes over NVLink
     if rank == 0:
         max_ms = float(allst[:, 0].max())
@@ -577,7 +590,8 @@ def run_native(args, rank, local_rank, world):
         e2e_fps = ne * world * Ke / (max_e2e / 1e3)
         h2d_step, d2h_step = float(allst[:, 8].sum()), float(allst[:, 9].sum())
         link_h2d, link_d2h = float(allst[:, 6].min()), float(allst[:, 7].min())
-        ceiling = ne * world / (float(allst[:, 11].max()) / 1e3)      # frames/s if a step were nothing but its copies
+        ceiling = ne * world / (float(allst[:, 11].max()) / 1e3)      # frames/s if a step were nothing but its H2D copies
+        mix_fps = ne * world / (float(allst[:, 12].max()) / 1e3)      # ... its H2D and D2H copies, started together
         line = {
             "metric": "map-update frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": cfg["scaling"],
@@ -593,10 +607,12 @@ def run_native(args, rank, local_rank, world):
                     "api": "wsmg_map_update_host_ex (pinned host buffers, chunked H2D/compute/D2H), a new frame per env per step",
                     "mode": args.e2e_mode, "numa_node_rank0": numa_node, "numa_note": numa_note,
                     "h2d_bytes_per_step_dense": float(allst[:, 10].sum()),
-                    "pcie_ceiling_gbs": {"h2d": link_h2d, "d2h": link_d2h,
-                                         "how": "pinned cudaMemcpyAsync of one e2e step's byte mix (h2d_bytes_per_step in, d2h_bytes_per_step "
-                                                "out, two streams at once), all ranks together; GB/s = min over ranks, ceiling = envs / slowest rank's time"},
-                    "pcie_ceiling_frames_per_s": ceiling, "frac_of_pcie_ceiling": e2e_fps / ceiling},
+                    "pcie_ceiling_gbs": {"h2d_alone": float(allst[:, 13].min()), "h2d_in_mix": link_h2d, "d2h_in_mix": link_d2h,
+                                         "how": "pinned cudaMemcpyAsync of one e2e step's bytes, all ranks together, GB/s = min over ranks: "
+                                                "h2d_alone = the step's H2D bytes with nothing going back (the ceiling: no pipeline can beat it); "
+                                                "in_mix = H2D and D2H bytes on two streams at once (estimate for a perfectly overlapped pipeline)"},
+                    "pcie_ceiling_frames_per_s": ceiling, "frac_of_pcie_ceiling": e2e_fps / ceiling,
+                    "pcie_mix_frames_per_s": mix_fps},
             "gpu_launches": 2 * K * world,               # k_cells (+ reset / rotation-setup blocks) and k_fused per step and rank
             "clocks": clk.summary(),
             "checksums": [float(x) for x in allst[:, 3]],
