@@ -13,11 +13,11 @@ echo "== bench env8"; timeout 600 python bench.py --workload env8 --no-cpu-basel
 if [ "$MODE" = "full" ]; then
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
-      python bench.py --envs 256 --steps 4 --warmup 3 --no-cpu-baseline --e2e-envs 16 --e2e-steps 2 --no-by-depth > $OUT/ncu_bench.log 2>&1
+      python bench.py --envs 256 --steps 4 --warmup 3 --no-cpu-baseline --e2e-envs 16 --e2e-steps 2 --no-by-depth --no-small-batch > $OUT/ncu_bench.log 2>&1
   grep -E "k_fused|k_cells|k_reset" $OUT/launches.csv | tail -12
   echo "== ncu full k_fused"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 4 -c 2 -f -o $OUT/prof_fused \
-      python bench.py --envs 256 --steps 4 --warmup 3 --no-cpu-baseline --e2e-envs 16 --e2e-steps 2 --no-by-depth > $OUT/ncu_full.log 2>&1
+      python bench.py --envs 256 --steps 4 --warmup 3 --no-cpu-baseline --e2e-envs 16 --e2e-steps 2 --no-by-depth --no-small-batch > $OUT/ncu_full.log 2>&1
   ls -la $OUT/*.ncu-rep
   [ -f ws-mgmap_b200/lib/libwsmg_phaseskip.so ] && { echo "== phase split"; timeout 600 python scripts/phase_split.py > $OUT/phase_split.txt 2>&1; tail -3 $OUT/phase_split.txt; }
   echo "== racecheck (small)"
