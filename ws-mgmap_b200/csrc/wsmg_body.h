@@ -17,14 +17,14 @@
 //     for which a non-negative float is its own key (profiles/: match_any+redux aggregation is 39x slower);
 //     its loop is statically strided and unrolled so that queues and slots are register names.
 //
-// Round 2 measured eight restructurings of this body and kept none of them (summaries under profiles/r02_*, DESIGN.md
+// Round 2 measured nine restructurings of this body and kept none of them (summaries under profiles/r02_*, DESIGN.md
 // section 5): two 512-thread CTAs per SM (crop rows in an L2-resident slot, tiled output rotation: +24 % instructions,
 // 3.91 -> 4.45 ms), per-env plan tables (taps / weights precomputed once per env: the extra 16-byte load per cell costs
 // more than the arithmetic it replaces), the output rotation run beside the band loop by the warps that do not own a
 // window cell (the two phases stay additive), L2 prefetch of the scatter's feature chunks, a separate scatter kernel at
 // two CTAs per SM, several slabs per CTA (the slab loop alone costs 0.29 ms: ptxas allocates the scatter's 64
 // registers differently), the ego rows leaving through shared memory + bulk copies (400 small bulk copies per CTA cost
-// 1 ms per 1024 envs).  What was kept: the band loop runs on the 26 warps that own a cell.
+// 1 ms per 1024 envs), the first rotation over a list of the tiles that can see the fan.  What was kept: the band loop runs on the 26 warps that own a cell.
 //
 // Shared memory (E=100, G=240: 229 KB of the 227 KiB a CTA may opt in to):
 //   X     [1 + E*E] F4    zero cell + (during the scatter) the per-thread cp.async feature slots, then the
