@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",                 # FMAs only where the arithmetic contract writes fmaf()
     "--expt-relaxed-constexpr", "--extended-lambda",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-ldl",
 ]
 
 

@@ -10,11 +10,14 @@
 // No tensor cores: the path is gather / scatter-max / bilinear streaming (~0.3 flop/byte).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+
+#include <vector>
 
 #include "wsmg_body.h"
 #include "wsmg_host.h"
@@ -615,6 +618,50 @@ static int host_lanes(HostLanes** out) {
   return 0;
 }
 
+// All host -> device copies of one chunk as ONE cudaMemcpyBatchAsync (CUDA runtime >= 12.8, looked up at run time).
+// Measured on PCIe Gen5 (profiles/r02_e2e_chunks.txt): every additional multi-megabyte cudaMemcpy(2D)Async leaves the
+// H2D engine idle for ~17 us, which with one feature copy per env (row skipping) costs 9 % of a PCIe-bound step; the
+// batch submits a chunk's large copies -- per env and plane the live rows, and the depth frames -- in one go
+// (5.57 k -> 6.00 k frames/s at 128 envs per step, 94 % of the H2D bound).  WSMG_HOST_NO_BATCHCOPY=1 or an older runtime: one call per copy.
+struct H2DList {
+  std::vector<void*> dst, src;
+  std::vector<size_t> size;
+  void clear() { dst.clear(); src.clear(); size.clear(); }
+  void add(void* d, const void* s, size_t bytes) {
+    if (bytes == 0) return;
+    dst.push_back(d); src.push_back(const_cast<void*>(s)); size.push_back(bytes);
+  }
+};
+typedef cudaError_t (*memcpy_batch_fn)(void**, void**, size_t*, size_t, cudaMemcpyAttributes*, size_t*, size_t, size_t*, cudaStream_t);
+static memcpy_batch_fn memcpy_batch() {
+  static const memcpy_batch_fn fn = [] {
+    const char* off = getenv("WSMG_HOST_NO_BATCHCOPY");
+    if (off && off[0] == '1') return (memcpy_batch_fn) nullptr;
+    // the CUDA runtime this library is bound to (it may sit in a local dlopen scope: look it up through one of its symbols)
+    Dl_info info;
+    void* h = nullptr;
+    if (dladdr(reinterpret_cast<void*>(&cudaMemcpyAsync), &info) != 0 && info.dli_fname != nullptr)
+      h = dlopen(info.dli_fname, RTLD_LAZY | RTLD_NOLOAD);
+    void* sym = h != nullptr ? dlsym(h, "cudaMemcpyBatchAsync") : dlsym(RTLD_DEFAULT, "cudaMemcpyBatchAsync");
+    return (memcpy_batch_fn)sym;
+  }();
+  return fn;
+}
+static cudaError_t submit_h2d(H2DList& l, cudaStream_t s) {
+  if (l.dst.empty()) return cudaSuccess;
+  if (memcpy_batch_fn fn = memcpy_batch()) {
+    cudaMemcpyAttributes at{};
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;      // the host buffers are read in stream order, like cudaMemcpyAsync does
+    size_t first = 0, fail = 0;
+    return fn(l.dst.data(), l.src.data(), l.size.data(), l.dst.size(), &at, &first, 1, &fail, s);
+  }
+  for (size_t i = 0; i < l.dst.size(); ++i) {
+    cudaError_t e = cudaMemcpyAsync(l.dst[i], l.src[i], l.size[i], cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // staging layout per chunk slot (2 slots): feat | depth | gps | compass | mask | ego | scratch
 struct HostSlot { float *feat, *depth, *gps, *compass, *mask, *ego; void* scratch; size_t scratch_bytes; };
 
@@ -759,6 +806,9 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
     slot_bytes(d, chunk, &hs, (unsigned char*)staging + slot * one);
     cudaStream_t s = st[slot];
     const size_t fe = (size_t)(d->C_in > 0 ? d->C_in : d->C) * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
+    static thread_local H2DList h2d;
+    h2d.clear();
+    const bool batched = memcpy_batch() != nullptr;
     if (feat_mapped != nullptr) {
       // nothing to stage
     } else if (flags & WSMG_HOST_SKIP_DEAD_ROWS) {
@@ -772,19 +822,27 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
         const size_t first = (size_t)lo * d->Wf;
         if (d->feat_nhwc) {                                      // rows lo..hi of an NHWC frame are one contiguous span
           const size_t off = first * planes, cnt = (size_t)(hi - lo + 1) * d->Wf * planes;
-          ck(cudaMemcpyAsync(hs.feat + (size_t)k * fe + off, feat_host + (size_t)(b0 + k) * fe + off, cnt * 4, cudaMemcpyHostToDevice, s));
+          h2d.add(hs.feat + (size_t)k * fe + off, feat_host + (size_t)(b0 + k) * fe + off, cnt * 4);
           continue;
         }
-        ck(cudaMemcpy2DAsync(hs.feat + (size_t)k * fe + first, pitch, feat_host + (size_t)(b0 + k) * fe + first, pitch,
-                             (size_t)(hi - lo + 1) * d->Wf * 4, planes, cudaMemcpyHostToDevice, s));
+        if (batched) {                                           // the live rows of every plane: `planes` spans per env
+          for (int pl = 0; pl < planes; ++pl)
+            h2d.add(hs.feat + (size_t)k * fe + (size_t)pl * d->Hf * d->Wf + first,
+                    feat_host + (size_t)(b0 + k) * fe + (size_t)pl * d->Hf * d->Wf + first, (size_t)(hi - lo + 1) * d->Wf * 4);
+        } else {
+          ck(cudaMemcpy2DAsync(hs.feat + (size_t)k * fe + first, pitch, feat_host + (size_t)(b0 + k) * fe + first, pitch,
+                               (size_t)(hi - lo + 1) * d->Wf * 4, planes, cudaMemcpyHostToDevice, s));
+        }
       }
     } else {
-      ck(cudaMemcpyAsync(hs.feat, feat_host + b0 * fe, n * fe * 4, cudaMemcpyHostToDevice, s));
+      h2d.add(hs.feat, feat_host + b0 * fe, n * fe * 4);
     }
-    ck(cudaMemcpyAsync(hs.depth, depth_host + b0 * de, n * de * 4, cudaMemcpyHostToDevice, s));
-    ck(cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, n * 2 * 4, cudaMemcpyHostToDevice, s));
-    ck(cudaMemcpyAsync(hs.compass, compass_host + b0, n * 4, cudaMemcpyHostToDevice, s));
-    ck(cudaMemcpyAsync(hs.mask, mask_host + b0, n * 4, cudaMemcpyHostToDevice, s));
+    h2d.add(hs.depth, depth_host + b0 * de, n * de * 4);
+    ck(submit_h2d(h2d, s));
+    // (the few bytes of pose stay ordinary copies: inside the batch they cost 20 % of the step, measured)
+    ck(cudaMemcpyAsync(hs.gps, gps_host + b0 * 2, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, s));
+    ck(cudaMemcpyAsync(hs.compass, compass_host + b0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    ck(cudaMemcpyAsync(hs.mask, mask_host + b0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     if (rc != 0) break;
     wsmg_dims dc = *d; dc.bs = n; dc.n_maps = n;
     rc = wsmg_map_update(feat_mapped != nullptr ? feat_mapped + b0 * fe : hs.feat, hs.depth, hs.gps, hs.compass, hs.mask, gmap + b0 * per_map, hs.ego, nullptr,
