@@ -649,11 +649,17 @@ static memcpy_batch_fn memcpy_batch() {
 }
 static cudaError_t submit_h2d(H2DList& l, cudaStream_t s) {
   if (l.dst.empty()) return cudaSuccess;
-  if (memcpy_batch_fn fn = memcpy_batch()) {
+  static bool batch_refused = false;       // the runtime has the entry point but turned the call down once: stay with single copies
+  memcpy_batch_fn fn = batch_refused ? nullptr : memcpy_batch();
+  if (fn != nullptr) {
     cudaMemcpyAttributes at{};
     at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;      // the host buffers are read in stream order, like cudaMemcpyAsync does
     size_t first = 0, fail = 0;
-    return fn(l.dst.data(), l.src.data(), l.size.data(), l.dst.size(), &at, &first, 1, &fail, s);
+    const cudaError_t e = fn(l.dst.data(), l.src.data(), l.size.data(), l.dst.size(), &at, &first, 1, &fail, s);
+    if (e == cudaSuccess) return e;
+    if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue) return e;
+    cudaGetLastError();                    // argument-level refusal: nothing was enqueued, redo the chunk copy by copy
+    batch_refused = true;
   }
   for (size_t i = 0; i < l.dst.size(); ++i) {
     cudaError_t e = cudaMemcpyAsync(l.dst[i], l.src[i], l.size[i], cudaMemcpyHostToDevice, s);
@@ -808,7 +814,7 @@ int wsmg_map_update_host_ex(const float* feat_host, const float* depth_host, con
     const size_t fe = (size_t)(d->C_in > 0 ? d->C_in : d->C) * d->Hf * d->Wf, de = (size_t)d->Hd * d->Wd, ee = (size_t)d->C * d->E * d->E;
     static thread_local H2DList h2d;
     h2d.clear();
-    const bool batched = memcpy_batch() != nullptr;
+    const bool batched = memcpy_batch() != nullptr;       // (a refusal at submit time falls back to one 1-D copy per plane)
     if (feat_mapped != nullptr) {
       // nothing to stage
     } else if (flags & WSMG_HOST_SKIP_DEAD_ROWS) {
