@@ -122,7 +122,9 @@ def test_trajectory_100_steps_vs_oracle():
 
 
 @pytest.mark.parametrize("c,hf,hd,e,gl,res", [(27, 32, 32, 100, 240, 0.12), (4, 40, 48, 61, 150, 0.2), (64, 256, 256, 100, 240, 0.12),
-                                                (8, 48, 64, 101, 260, 0.1), (4, 24, 24, 30, 64, 0.3), (12, 56, 64, 96, 208, 0.15)])   # 101: the largest ego grid one SM holds
+                                                (8, 48, 64, 101, 260, 0.1), (4, 24, 24, 30, 64, 0.3), (12, 56, 64, 96, 208, 0.15),
+                                                (27, 256, 256, 100, 240, 0.12), (6, 224, 256, 100, 240, 0.12)])
+# 101: the largest ego grid one SM holds; the last two: C % 4 != 0 at the reference's grid sizes (compile-time-geometry builds of their own)
 def test_other_geometries_vs_spec(c, hf, hd, e, gl, res):
     from oracle.mapping_oracle import spec_step
     geo = MapGeometry(resolution=res, ego=e, glob=gl)

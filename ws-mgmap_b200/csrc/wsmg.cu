@@ -463,6 +463,12 @@ static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s, bool 
     return launch_fused_t<100, 240, 256 * 256, true, true>(p, grid, s, di.dev, pdl);
   }
   if (vec) return tma ? launch_fused_t<0, 0, 0, true, true>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false>(p, grid, s, di.dev, pdl);
+  // C % 4 != 0 (no 16-byte cells, no TMA) at the reference's grid sizes: compile-time geometry as well -- the run-time
+  // build spends a third of its instructions on integer divisions by E, E + 2 and the tile counts
+  if (p.g.E == 100 && p.g.G == 240 && !sw.generic) {
+    if (p.g.Hf * p.g.Wf == 224 * 224) return launch_fused_t<100, 240, 224 * 224, false, false>(p, grid, s, di.dev, pdl);
+    if (p.g.Hf * p.g.Wf == 256 * 256) return launch_fused_t<100, 240, 256 * 256, false, false>(p, grid, s, di.dev, pdl);
+  }
   return launch_fused_t<0, 0, 0, false, false>(p, grid, s, di.dev, pdl);
 }
 

@@ -440,20 +440,29 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
           tma_load_box(ring + 1 + ((uu + S0) % RR) * WWP, &p.tmap, c0, v0, u0 + uu, mrow, &bars[k]);
         }
       }
-    } else {
+    } else if (VEC) {
       for (int t = tid; t < BAND * WW; t += NT) {
         int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
         if (uu < WW) {
           int u = u0 + uu, v = v0 + vv;
           bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
           const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
-          F4* dst = ring + 1 + ((uu + S0) % RR) * WWP + vv;
-          if (VEC) {
-            async_copy16(dst, src, inside);
-          } else {
-#pragma unroll
-            for (int ch = 0; ch < SLAB; ++ch) async_copy4(&dst->v[ch], src + (ch < nch ? ch : 0), inside && ch < nch);
-          }
+          async_copy16(ring + 1 + ((uu + S0) % RR) * WWP + vv, src, inside);
+        }
+      }
+      async_commit();
+    } else {
+      // C % 4 != 0: the cells are only 4-byte aligned, so the window moves one float per copy.  Consecutive lanes take the
+      // consecutive floats of a cell (item = cell * 4 + channel): a warp instruction then touches 8 cells' 16-byte
+      // pieces instead of one float in each of 32 cells -- a quarter of the L1 tag lookups.
+      for (int t = tid; t < BAND * WW * SLAB; t += NT) {
+        const int cell = t / SLAB, ch = t - cell * SLAB;
+        int rr = cell / WW, vv = cell - rr * WW, uu = k * BAND + rr;
+        if (uu < WW) {
+          int u = u0 + uu, v = v0 + vv;
+          bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G && ch < nch;
+          const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C + ch : 0);
+          async_copy4(&(ring + 1 + ((uu + S0) % RR) * WWP + vv)->v[ch], src, inside);
         }
       }
       async_commit();
