@@ -220,6 +220,42 @@ def test_stage_composition_and_host_pipeline():
         pipe0.step(feat.clone(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g4, ego_h)
 
 
+def test_host_pipeline_without_batched_copies():
+    """The host-buffer entry submits a chunk's large copies as one cudaMemcpyBatchAsync when the runtime has it; an older
+    runtime (or WSMG_HOST_NO_BATCHCOPY=1, read once per process -- hence the subprocess) takes one call per copy.  Both ways,
+    in all three copy modes, the ego map and the global map are the direct update's, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import wsmgmap_b200
+from wsmgmap_b200 import ops
+from wsmgmap_b200.synth import make_depth, make_features
+dev = torch.device('cuda', 0)
+bs, c, hf, hd = 7, 64, 224, 256
+gen = torch.Generator().manual_seed(5)
+feat = make_features(bs, c, hf, hf, gen); depth = make_depth('room2', bs, hd, hd, gen)
+depth[3] = make_depth('uniform', 1, hd, hd, gen)[0]
+gps = torch.randn(bs, 2, generator=gen); compass = torch.rand(bs, 1, generator=gen) * 6 - 3; masks = torch.zeros(bs, 1)
+g0 = torch.zeros(bs, 240, 240, c, device=dev)
+ego0 = ops.map_update(feat.to(dev), depth.to(dev), gps.to(dev), compass.to(dev), masks.to(dev), g0)
+d = ops.dims_for(feat.shape, depth.shape, bs)
+for kw in (dict(), dict(skip_dead_rows=True), dict(zero_copy=True)):
+    pipe = ops.HostPipeline(d, dev, chunk_envs=3, **kw)
+    g = torch.zeros(bs, 240, 240, c, device=dev)
+    ego_h = torch.empty(bs, c, 100, 100).pin_memory()
+    pipe.step(feat.pin_memory(), depth.pin_memory(), gps.pin_memory(), compass.pin_memory(), masks.pin_memory(), g, ego_h)
+    torch.cuda.synchronize()
+    assert torch.equal(ego_h, ego0.cpu()) and torch.equal(g, g0), kw
+print('ok')
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({}, {"WSMG_HOST_NO_BATCHCOPY": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (env, r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_full_size_properties():
     """Size-independent properties at a batch the oracle would need minutes for (256 envs):
     max-fusion is idempotent, the map is monotone, a reset forgets everything, batch order is irrelevant."""
