@@ -14,8 +14,10 @@ def build(specs):
     for f in glob.glob(os.path.join(LIBDIR, "libwsmg_var_*.so*")):
         os.remove(f)
     for spec in specs:
-        name, _, defs = spec.partition(":")
-        print(build_cuda(force=True, phase_skip=True, variant="var_" + name, defines=[d for d in defs.split(",") if d]))
+        name, _, rest = spec.partition(":")          # name:DEF1,DEF2[;nvcc-flag;nvcc-flag]
+        defs, _, fl = rest.partition(";")
+        print(build_cuda(force=True, phase_skip=True, variant="var_" + name, defines=[d for d in defs.split(",") if d],
+                         flags=[f for f in fl.split(";") if f]))
 
 def child(envs):
     import torch

@@ -54,7 +54,7 @@ def _sources():
     return out
 
 
-def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = False, variant: str = "", defines=()) -> str:
+def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = False, variant: str = "", defines=(), flags=()) -> str:
     """phase_skip=True builds the profiling variant lib/libwsmg_phaseskip.so (-DWSMG_PHASE_SKIP, see
     csrc/wsmg_body.h: WSMG_SKIP); load it with WSMG_LIB_PATH, never in production.  `variant` + `defines` build an
     experiment library lib/libwsmg_<variant>.so with extra -D switches (scripts/variants.py)."""
@@ -68,6 +68,8 @@ def build_cuda(verbose: bool = False, force: bool = False, phase_skip: bool = Fa
         cmd.insert(1, "-Xptxas=-v")
     for d in defines:
         cmd.insert(1, "-D" + d)
+    for f in flags:
+        cmd.insert(1, f)
     if phase_skip:
         cmd.insert(1, "-DWSMG_PHASE_SKIP")
     r = subprocess.run(cmd, capture_output=True, text=True)
