@@ -84,6 +84,7 @@ struct SmemPlan {
   int rr;         // ring rows
   int s0;         // ring slot of window row 0 (first slot beyond the key planes)
   int wwp;        // ring row stride in cells (row bytes are a multiple of 128 for TMA)
+  uint32_t m_rr;  // fd_magic(rr)
 };
 constexpr int MAX_BANDS = 18;
 
@@ -101,6 +102,7 @@ WSMG_HD SmemPlan make_plan(const Geo& g) {
   s.npp = npp_of(g.fan_cells);
   s.s0 = round_rows((s.npp + s.wwp - 1) / s.wwp);
   s.rr = round_rows(4 * BAND + 2 > s.s0 + BAND ? 4 * BAND + 2 : s.s0 + BAND);
+  s.m_rr = fd_magic(s.rr);
   s.x_off = 0;
   int x_cells = 1 + g.E * g.E;                               // X also hosts the scatter's staging slots
   if (x_cells < 1 + SCATTER_STAGES * SLAB * FUSED_NT) x_cells = 1 + SCATTER_STAGES * SLAB * FUSED_NT;
@@ -230,10 +232,10 @@ WSMG_HD F4 tap(const F4* base, int idx) { return idx > 0 ? base[idx] : f4_zero()
 // land on ~1.6 distinct 16-byte bank groups per wavefront instead of ~2.1 for 8 cells in a row (simulated
 // over random headings and confirmed by ncu), and a row of the tile is still one full 32-byte sector of
 // the NCHW output.  slot = tile * 32 + lane; returns false for the padding of ragged tiles.
-WSMG_HD bool tile_cell(int slot, int E, int* i, int* j) {
+WSMG_HD bool tile_cell(int slot, int E, int* i, int* j, uint32_t m_tiles = 0u) {
   const int tile = slot >> 5, l = slot & 31;
   const int tiles_x = (E + 7) >> 3;
-  const int band = tile / tiles_x, tcol = tile - band * tiles_x;
+  const int band = fd_div(tile, tiles_x, m_tiles), tcol = tile - band * tiles_x;
   const int q = l >> 3, k = l & 7;
   *j = 8 * tcol + 4 * (q & 1) + (k & 3);
   *i = 4 * band + 2 * (q >> 1) + (k >> 2);
@@ -338,6 +340,9 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   const int paste_lo = G / 2 - E / 2;
   const float half_e = (float)E / 2.0f, half_g = (float)G / 2.0f, gcenter = (float)(G / 2);
   const int NB = (WW + BAND - 1) / BAND;          // <= MAX_BANDS - 1 (validated on the host)
+  // divisions by run-time geometry go through fd_div (compile-time geometry: plain constants, m = 0)
+  const uint32_t mE = CE > 0 ? 0u : g.m_E, mWW = CE > 0 ? 0u : g.m_WW, mT = CE > 0 ? 0u : g.m_tiles, mRR = CE > 0 ? 0u : sp.m_rr;
+  auto ring_slot = [&](int r) -> int { const int x = r + S0; return x - fd_div(x, RR, mRR) * RR; };   // (r + S0) % RR
 
   F4* X = reinterpret_cast<F4*>(smem + sp.x_off);            // X[0] = zero cell, R/B(y,x) at X[1 + y*E + x]
   int32_t* Pk = reinterpret_cast<int32_t*>(smem + sp.r2_off);
@@ -437,17 +442,17 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
 #endif
         if (tma_lane < boxes) {
           const int uu = k * BAND + tma_lane * TMA_ROWS;
-          tma_load_box(ring + 1 + ((uu + S0) % RR) * WWP, &p.tmap, c0, v0, u0 + uu, mrow, &bars[k]);
+          tma_load_box(ring + 1 + ring_slot(uu) * WWP, &p.tmap, c0, v0, u0 + uu, mrow, &bars[k]);
         }
       }
     } else if (VEC) {
       for (int t = tid; t < BAND * WW; t += NT) {
-        int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
+        int rr = fd_div(t, WW, mWW), vv = t - rr * WW, uu = k * BAND + rr;
         if (uu < WW) {
           int u = u0 + uu, v = v0 + vv;
           bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G;
           const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C : 0);
-          async_copy16(ring + 1 + ((uu + S0) % RR) * WWP + vv, src, inside);
+          async_copy16(ring + 1 + ring_slot(uu) * WWP + vv, src, inside);
         }
       }
       async_commit();
@@ -457,12 +462,12 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       // pieces instead of one float in each of 32 cells -- a quarter of the L1 tag lookups.
       for (int t = tid; t < BAND * WW * SLAB; t += NT) {
         const int cell = t / SLAB, ch = t - cell * SLAB;
-        int rr = cell / WW, vv = cell - rr * WW, uu = k * BAND + rr;
+        int rr = fd_div(cell, WW, mWW), vv = cell - rr * WW, uu = k * BAND + rr;
         if (uu < WW) {
           int u = u0 + uu, v = v0 + vv;
           bool inside = (unsigned)u < (unsigned)G && (unsigned)v < (unsigned)G && ch < nch;
           const float* src = gmap_b + (inside ? ((size_t)u * G + v) * C + ch : 0);
-          async_copy4(&(ring + 1 + ((uu + S0) % RR) * WWP + vv)->v[ch], src, inside);
+          async_copy4(&(ring + 1 + ring_slot(uu) * WWP + vv)->v[ch], src, inside);
         }
       }
       async_commit();
@@ -679,7 +684,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   if (p.proj_out != nullptr) {
     float* dst = p.proj_out + ((size_t)b * C + c0) * EE;
     for (int t = tid; t < EE; t += NT) {
-      int y = t / E, x = t - y * E;
+      int y = fd_div(t, E, mE), x = t - y * E;
       F4 v = Pf[fan_idx(fanrow[y], x)];
 #pragma unroll
       for (int ch = 0; ch < SLAB; ++ch)
@@ -697,7 +702,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     const int slot = s0 + tid;
     bool hit = false;
     int i = 0, j = 0;
-    bool in_tile = slot < nslots && tile_cell(slot, E, &i, &j);
+    bool in_tile = slot < nslots && tile_cell(slot, E, &i, &j, mT);
     if (in_tile) {
       const int hr = hitrow[i];
       if (j < (hr & 0xFFFF) || j >= (hr >> 16)) { X[1 + i * E + j] = f4_zero(); in_tile = false; }   // cannot see the fan
@@ -733,7 +738,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
         const unsigned mr = ((m >> a) & 0xFu) | (((m >> (a + 8)) & 0xFu) << 4);
         if (mr != 0u) {
           const int tile = (s0 + tid) >> 5, tiles_x = (E + 7) >> 3;
-          const int band = tile / tiles_x, j0 = 8 * (tile - band * tiles_x), row = 4 * band + lane;
+          const int band = fd_div(tile, tiles_x, mT), j0 = 8 * (tile - band * tiles_x), row = 4 * band + lane;
           atomicMin(&ext[row].a, j0 + __ffs(mr) - 1);
           atomicMax(&ext[row].b, j0 + 31 - __clz(mr));
         }
@@ -771,13 +776,13 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
       int y0 = tp.i0 - paste_lo;
       rt.a = (unsigned)y0 < (unsigned)E ? 1 + y0 * E : NEG;
       rt.b = ((unsigned)(y0 + 1) < (unsigned)E && tp.w1 != 0.0f) ? 1 + (y0 + 1) * E : NEG;
-      rt.c = as_int(tp.w1); rt.d = 1 + ((t + S0) % RR) * WWP;
+      rt.c = as_int(tp.w1); rt.d = 1 + ring_slot(t) * WWP;
     }
     rowT[t] = rt;
     {  // columns of R that can contribute to window row t: union of the extents of its (up to) two source rows
       I2 e; e.a = E; e.b = -1;
-      if (rt.a > 0) { I2 s0e = ext[(rt.a - 1) / E]; e = s0e; }
-      if (rt.b > 0) { I2 s1e = ext[(rt.b - 1) / E]; e.a = s1e.a < e.a ? s1e.a : e.a; e.b = s1e.b > e.b ? s1e.b : e.b; }
+      if (rt.a > 0) { I2 s0e = ext[fd_div(rt.a - 1, E, mE)]; e = s0e; }
+      if (rt.b > 0) { I2 s1e = ext[fd_div(rt.b - 1, E, mE)]; e.a = s1e.a < e.a ? s1e.a : e.a; e.b = s1e.b > e.b ? s1e.b : e.b; }
       rowE[t] = e;
     }
   }
@@ -790,8 +795,8 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     bXT[t] = bx;
     Tap1D tq = make_tap(unnormalize(base_coord(t + paste_lo, G) + qy, half_g));
     int ry = tq.i0 - u0;
-    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + ((ry + S0) % RR) * WWP : NEG;
-    by.b = ((unsigned)(ry + 1) < (unsigned)WW && tq.w1 != 0.0f) ? 1 + ((ry + 1 + S0) % RR) * WWP : NEG;
+    I4 by; by.a = (unsigned)ry < (unsigned)WW ? 1 + ring_slot(ry) * WWP : NEG;
+    by.b = ((unsigned)(ry + 1) < (unsigned)WW && tq.w1 != 0.0f) ? 1 + ring_slot(ry + 1) * WWP : NEG;
     by.c = as_int(tq.w1); by.d = 0;
     bYT[t] = by;
   }
@@ -806,7 +811,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   int p_lo = 0;
   auto fuse_band = [&](int k) {                              // 3a: F rows of band k, in place in the ring
     for (int t = tid; t < BAND * WW; t += LT) {
-      int rr = t / WW, vv = t - rr * WW, uu = k * BAND + rr;
+      int rr = fd_div(t, WW, mWW), vv = t - rr * WW, uu = k * BAND + rr;
       if (uu >= WW) continue;
       const I4 ct = colT[vv], rt = rowT[uu];
       const int cell = rt.d + vv;
@@ -845,7 +850,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
     int done = k * BAND < WW ? k * BAND : WW;
     int p_hi = done - 2 > p_lo ? done - 2 : p_lo;
     for (int t = tid; t < (p_hi - p_lo) * E; t += LT) {
-      int dr = t / E, q = t - dr * E, pr = p_lo + dr;
+      int dr = fd_div(t, E, mE), q = t - dr * E, pr = p_lo + dr;
       const I4 bx = bXT[q], by = bYT[pr];
       Weights w = make_weights(as_float(bx.c), as_float(by.c));
       F4 a = tap(ring, by.a + bx.a), bb = tap(ring, by.a + bx.b), c = tap(ring, by.b + bx.a), d = tap(ring, by.b + bx.b);
@@ -884,7 +889,7 @@ WSMG_BODY void fused_body(const FusedParams& p, int block, unsigned char* smem, 
   float* ego_b = p.ego + ((size_t)b * C + c0) * EE;
   for (int slot = tid; slot < (WSMG_SKIP(8) ? 0 : nslots); slot += NT) {
     int i, j;
-    if (!tile_cell(slot, E, &i, &j)) continue;
+    if (!tile_cell(slot, E, &i, &j, mT)) continue;
     const int t = i * E + j;
     float ix, iy;
     rot_coords(baseE[j], baseE[i], cs, sn, half_e, &ix, &iy);

@@ -47,6 +47,7 @@ inline Geo make_geo(const wsmg_dims* d) {
   g.half_g = (float)d->G / 2.0f;
   g.gcenter = (float)(d->G / 2);                               // G//2
   g.paste_lo = d->G / 2 - d->E / 2;                            // rgb_mapping.py:42
+  g.m_E = fd_magic(d->E); g.m_WW = fd_magic(d->E + 2); g.m_tiles = fd_magic((d->E + 7) >> 3);
   int ymax = d->E / 2;                                         // rint((E-1)/2 - a) <= ceil((E-1)/2) for a > 0
   g.fan_rows = ymax + 1 < d->E ? ymax + 1 : d->E;
   g.fan_cells = 0;

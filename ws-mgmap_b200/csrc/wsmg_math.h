@@ -37,7 +37,21 @@ struct Geo {
   double inv_cell;       // 1.0 / (double)cell, see div_cell()
   float half_e, half_g;  // E/2, G/2 (grid_sampler scaling factor)
   float gcenter;         // G//2                                   rgb_mapping.py:47
+  uint32_t m_E, m_WW, m_tiles;   // fd_magic of E, E + 2 and the tile columns (E + 7) / 8: run-time-geometry builds divide by multiplying
 };
+
+// n / d as a multiplication for the run-time-geometry builds (a third of their instructions were integer divisions):
+// with m = ceil(2^32 / d), (n * m) >> 32 == n / d whenever n * d < 2^32 -- every use here has n < 2^13 and d < 2^8.
+// m == 0 (d <= 1, or a caller without the constant) falls back to the division.
+WSMG_HD uint32_t fd_magic(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)d - 1u) / (unsigned)d); }
+WSMG_HD int fd_div(int n, int d, uint32_t m) {
+  if (m == 0u) return n / d;
+#if defined(__CUDA_ARCH__)
+  return (int)__umulhi((unsigned)n, m);
+#else
+  return (int)(((unsigned long long)(unsigned)n * m) >> 32);
+#endif
+}
 
 // Packed "fan" layout of the scatter grid.  With depth >= 0 and the 90 degree pinhole
 // (|xx| <= 1), a pixel that lands in row y = rint(half - Z/cell) has
