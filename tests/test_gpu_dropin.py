@@ -92,6 +92,18 @@ def test_channel_rebinning_and_input_checks():
     assert _close(out.cpu(), want, 1.0)
     with pytest.raises(ValueError):
         m(feat.to(DEV), dict(depth=depth, gps=obs["gps"], compass=obs["compass"]), torch.zeros(2, 1, device=DEV))  # CPU depth
+    # a wider producer at the reference's shapes (96 -> 64 channels, uneven bins of 1 and 2): the compile-time-geometry build
+    m2 = RGBMapping(_cfg(2, 64))
+    feat2 = make_features(2, 96, 224, 224, gen, signed=True)
+    depth2 = make_depth("room2", 2, 256, 256, gen)
+    gps2, comp2 = torch.randn(2, 2, generator=gen), torch.rand(2, 1, generator=gen) * 6 - 3
+    obs2 = dict(depth=depth2.to(DEV), gps=gps2.to(DEV), compass=comp2.to(DEV))
+    out2 = m2(feat2.to(DEV), obs2, torch.zeros(2, 1, device=DEV))
+    pooled2 = torch.nn.functional.adaptive_max_pool1d(feat2.permute(0, 2, 3, 1).reshape(2, -1, 96), 64)
+    pooled2 = pooled2.reshape(2, 224, 224, 64).permute(0, 3, 1, 2).contiguous()
+    orc2 = OracleMapper(2, 64)
+    want2 = orc2.step(pooled2, depth2, gps2, comp2, torch.zeros(2, 1))
+    assert _close(out2.cpu(), want2, float(feat2.abs().max())) and _close(m2.full_global_map.cpu(), orc2.full_global_map, float(feat2.abs().max()))
 
 
 def test_channels_last_producer_is_consumed_as_is():

@@ -444,6 +444,8 @@ static int launch_fused(FusedParams p, const wsmg_dims* d, cudaStream_t s, bool 
     rc = encode_window_map(&p.tmap, p.gmap, d->n_maps, p.g, p.sp.wwp);
     if (rc != 0) return rc;
   }
+  if (p.g.Cin != p.g.C && vec && tma && p.g.E == 100 && p.g.G == 240 && p.g.Hf * p.g.Wf == 224 * 224 && !sw.generic)
+    return launch_fused_t<100, 240, 224 * 224, true, true, FEAT_POOL>(p, grid, s, di.dev, pdl);   // a wider producer at the reference's shapes
   if (p.g.Cin != p.g.C) {                                   // channel pool fused in the scatter: run-time geometry builds
     if (vec) return tma ? launch_fused_t<0, 0, 0, true, true, FEAT_POOL>(p, grid, s, di.dev, pdl) : launch_fused_t<0, 0, 0, true, false, FEAT_POOL>(p, grid, s, di.dev, pdl);
     return launch_fused_t<0, 0, 0, false, false, FEAT_POOL>(p, grid, s, di.dev, pdl);
